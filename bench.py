@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 acceleration path (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path, host cores
+
+Headline workload (BASELINE.json configs[4], the configuration the metric is quoted on): FP64 direct-sum
+force evaluation of a synthetic Plummer sphere, N = 2^20, softening 0.01; one "step" = one full force
+evaluation of all N particles.  N>1 GPUs: targets are sharded over ranks (strong scaling: total work fixed)
+and each step starts with the NCCL all-gather of the owned position shards.
+
+value  = ordered pair interactions per second, N(N-1)/t, particle state already resident in HBM
+e2e    = same metric through the reference-facing call with HOST buffers (H2D of x, m and D2H of a
+         inside the timed region): at N=1 literally the drop-in `acceleration()` symbol
+Also reported on the same line: roofline (FP64 pipe), cpu_baseline (compiled reference on the host, bounded
+sample), Barnes-Hut force-evaluation time ("bh"), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "fp64_direct_sum_pair_interactions_per_s"
+UNIT = "G interactions/s"
+FLOP_PER_INTERACTION = 20      # GPU-Gems-3 convention: 18 + rsqrt counted as 2
+FP64_OPS_PER_INTERACTION = 16  # FP64-pipe instructions our kernel actually issues per interaction
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12   # 37.2, used only if the live measurement fails
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--n", type=int, default=1 << 20, help="particles of the direct-sum workload")
+    p.add_argument("--eps", type=float, default=0.01)
+    p.add_argument("--ic", default="plummer", choices=["plummer", "uniform"])
+    p.add_argument("--bh-n", type=int, default=1 << 20, help="particles of the Barnes-Hut side measurement (0 = skip)")
+    p.add_argument("--cpu-n", type=int, default=1 << 16, help="particles of the bounded CPU-baseline sample (0 = skip)")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def make_ic(kind, n, seed=42):
+    from conftest import load_package
+    load_package()
+    from gravity_simulator_b200 import ics
+    return ics.plummer(n, seed) if kind == "plummer" else ics.uniform_cube(n, seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for k, nm in enumerate(names):
+                    if f[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm), power_note="see reasons")
+        out["reasons"] = sorted(reasons)
+        out.pop("power_note", None)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+
+def cpu_reference_time(n, eps, kind, reps=1):
+    """Seconds per pairwise force evaluation of the unmodified reference at size n (1 thread: the reference's
+    direct-sum code has no OpenMP).  Falls back to the oracle port if _ref is absent."""
+    from oracle.bind import Oracle, Reference
+    x, v, m, G = make_ic(kind, n)
+    if Reference.available():
+        impl, kname = Reference(), "reference"
+    else:
+        impl, kname = Oracle(), "port"
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        impl.acceleration(x, m, G, "pairwise", eps)
+        best = min(best, time.perf_counter() - t0)
+    return best, kname
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_n if args.cpu_n > 0 else 1 << 15
+    # bound the whole run to a few minutes: one evaluation at 2^16 takes ~13 s on one core
+    while n > 4096 and (args.steps + args.warmup) * 13.0 * (n / 65536.0) ** 2 > 150.0:
+        n //= 2
+    from oracle.bind import Oracle, Reference
+    x, v, m, G = make_ic(args.ic, n)
+    impl, kname = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
+    for _ in range(args.warmup):
+        impl.acceleration(x, m, G, "pairwise", args.eps)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        impl.acceleration(x, m, G, "pairwise", args.eps)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n * (n - 1) / dt / 1e9
+    sample = (f"pairwise force evaluation of the first-principles same workload at N={n} ({args.ic}, eps={args.eps}); "
+              f"interactions/s is size-independent for the O(N^2) loop; full N={args.n} would take ~{dt * (args.n / n) ** 2 / 60:.0f} min")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"direct-sum pairwise FP64, {args.ic} N={args.n}, eps={args.eps} (timed on a bounded sample N={n})"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kname, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+
+def run_b200_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus > 1 launch under torch.distributed.run (one process per GPU)")
+
+    from conftest import load_package
+    gb = load_package()
+
+    dist = None
+    uid = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(gb.Context.new_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(val):
+        if dist is None:
+            return val
+        import torch
+        t = torch.tensor([val], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.n
+    x, v, m, G = make_ic(args.ic, n)
+    ctx = gb.Context(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
+    ctx.set_system(x, m, G, v)
+    ctx.synchronize()
+
+    def step():
+        ctx.mark_positions_sharded()          # as after a drift: the gather is part of every force call
+        ctx.acceleration("pairwise", args.eps)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = gb.kernel_launch_count()
+    barrier()
+    ctx.synchronize()
+    dev_ms, kern_ms, gather_ms = 0.0, [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.flush_l2()                        # inputs (32 MiB) are smaller than L2: flush between timed iterations
+        ctx.event_record(0)
+        step()
+        ctx.event_record(1)
+        dev_ms += ctx.event_elapsed_ms(0, 1)  # CUDA events on the launching stream
+        kern_ms.append(ctx.timing_ms(2))
+        gather_ms.append(ctx.timing_ms(1))
+    ctx.synchronize()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = gb.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    ms_per_step = dev_ms / args.steps
+    inter = float(n) * float(n - 1)
+    value = inter / (ms_per_step * 1e-3) / 1e9
+
+    # roofline of the dominant kernel (direct_sum_kernel): FP64 pipe
+    lo, hi = ctx.owned_range()
+    k_ms = float(np.mean(kern_ms))
+    k_inter = float(hi - lo) * float(n - 1)
+    try:
+        peak_tf, peak_mhz = gb.measure_fp64_peak(local_rank)
+        peak_src = "measured live: register-resident DFMA loop (grav_b200_measure_fp64_peak)"
+    except Exception as e:  # pragma: no cover
+        peak_tf, peak_mhz, peak_src = NOMINAL_FP64_TFLOPS, 1965.0, f"nominal fallback ({e})"
+    ach_tf = FLOP_PER_INTERACTION * k_inter / (k_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+        "traffic": None, "kernel": "direct_sum_kernel<2,false>", "kernel_ms": k_ms,
+        "convention": f"{FLOP_PER_INTERACTION} flop per ordered interaction; peak = {peak_src} at {peak_mhz:.0f} MHz",
+        "fp64_pipe_util": FP64_OPS_PER_INTERACTION * k_inter / (k_ms * 1e-3) / (peak_tf * 1e12 / 2.0),
+        "fp64_pipe_util_note": f"{FP64_OPS_PER_INTERACTION} FP64-pipe instructions per interaction over the measured DFMA issue rate",
+    }
+
+    # end to end through the reference-facing call with host buffers
+    e2e = None
+    if not args.no_e2e:
+        a_host = np.empty((n, 3))
+        for arr in (x, m, a_host):
+            try:
+                gb.host_register(arr)
+            except Exception:
+                pass
+        if world == 1:
+            def e2e_step():
+                return gb.acceleration(x, m, G, "pairwise", args.eps)   # the drop-in acceleration() symbol
+        else:
+            def e2e_step():
+                ctx.set_system(x, m, G)
+                ctx.acceleration("pairwise", args.eps)
+                return ctx.accelerations(a_host)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(args.steps, 3))
+        for _ in range(ke):
+            out = e2e_step()
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / ke)
+        e2e = {"value": inter / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + m.nbytes),
+               "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": e2e_s * 1e3,
+               "api": "acceleration() in libgrav_sim_b200.so" if world == 1 else "grav_b200_ctx_set_system/_acceleration/_get_accelerations"}
+
+    # Barnes-Hut side measurement (second half of the metric): s per full force evaluation
+    bh = None
+    if args.bh_n > 0:
+        try:
+            xb, vb, mb, Gb = make_ic(args.ic, args.bh_n, seed=43)
+            ctx.set_system(xb, mb, Gb, vb)
+            for _ in range(2):
+                ctx.mark_positions_sharded()
+                ctx.acceleration("barnes_hut", args.eps, 0.5, 1)
+            ctx.synchronize()
+            barrier()
+            tt, stages = [], []
+            for _ in range(3):
+                ctx.flush_l2()
+                ctx.mark_positions_sharded()
+                ctx.event_record(2)
+                ctx.acceleration("barnes_hut", args.eps, 0.5, 1)
+                ctx.event_record(3)
+                tt.append(ctx.event_elapsed_ms(2, 3))
+                stages.append([ctx.timing_ms(s) for s in (1, 3, 4, 5, 2)])
+            bh_ms = max_over_ranks(float(np.mean(tt)))
+            st = np.mean(np.array(stages), axis=0)
+            bh = {"metric": "barnes_hut_force_eval_s_per_step", "value": bh_ms * 1e-3, "unit": "s", "n": args.bh_n,
+                  "theta": 0.5, "leaf": 1, "ic": args.ic, "mode": "reference-exact",
+                  "stage_ms": {"gather": st[0], "bbox_morton": st[1], "sort": st[2], "build": st[3], "walk": st[4]},
+                  "hbm_frac_algorithmic": (470.0 * args.bh_n / (bh_ms * 1e-3) / 1e9) / _hbm_peak()}
+        except gb.GravB200Error as e:
+            bh = {"unavailable": str(e)[:200]}
+
+    cpu = None
+    if rank == 0 and args.cpu_n > 0:
+        t_cpu, kname = cpu_reference_time(args.cpu_n, args.eps, args.ic)
+        cpu = {"value": args.cpu_n * (args.cpu_n - 1) / t_cpu / 1e9, "unit": UNIT, "cores": 1, "kind": kname,
+               "sample": f"one pairwise force evaluation at N={args.cpu_n} ({args.ic}, eps={args.eps}), {t_cpu:.1f} s on 1 core "
+                         f"(the reference's direct sum is single-threaded); rate is size-independent"}
+
+    ctx.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"direct-sum pairwise FP64 force evaluation, {args.ic} N={n}, eps={args.eps}",
+                       "partition": f"targets sharded over {world} rank(s), NCCL all-gather of positions per step" if world > 1 else "single GPU",
+                       "l2": "256 MiB L2 flush between timed iterations"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "bh": bh, "gpu_launches": int(launches),
+            "clocks": clocks, "allgather_ms": float(np.mean(gather_ms)) if world > 1 else 0.0,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"])
+    except Exception:
+        return 6650.0   # B200_PROFILING.md fallback
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,372 @@
+// FP64 O(N^2) direct sum on sm_100a.
+//
+// Replaces the j-loops of acceleration_pairwise (reference src/acceleration.c:198-231) and
+// acceleration_massless (:298-361).  Same mathematics -- a_i = -G sum_j m_j R_ij /
+// (|R_ij|^2 + eps^2)^{3/2}, R_ij = x_i - x_j, no self term -- but organised for the GPU:
+// every ordered interaction i<-j is evaluated (no Newton-3 scatter), i-accumulators live in
+// registers, sources stream through shared memory as packed (x,y,z,m) records, and G is
+// applied once at the end.
+//
+// Cost model (DESIGN.md "direct sum"): 16 FP64-pipe instructions per ordered interaction
+//   3 DADD  (dx,dy,dz)            3 DFMA (r2 = eps2 + dx^2 + dy^2 + dz^2)
+//   7       (r2^-3/2 * m_j from the MUFU.RSQ64H seed with one cubically convergent step)
+//   3 DFMA  (accumulate)
+// The seed y0 = rsqrt.approx.ftz.f64(r2) only looks at the high word of r2 (|e| <~ 2^-20 with
+// e = 1 - r2*y0^2); r2^-3/2 = y0^3 (1-e)^-3/2 = y0^3 (1 + e(3/2 + 15/8 e) + 35/16 e^3 + ...),
+// and the dropped term is < 2^-58, i.e. below double rounding.
+//
+// Work decomposition: "units" = (block of IB=256*TI targets) x (tile of 256 sources), flattened
+// target-block-major and split EVENLY over a persistent grid of sm_count*occupancy CTAs
+// (stream-K style), so there is no tail wave whatever N is.  A CTA whose range ends inside a
+// target block writes its partial sums to a scratch slot; a tiny fix-up kernel adds the slots
+// of each split block in CTA order, so results are deterministic (no floating-point atomics).
+#include "internal.cuh"
+
+namespace gb {
+
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// m_j * r2^(-3/2), 7 FP64-pipe instructions + 1 MUFU.
+__device__ __forceinline__ double inv_r3_times_m(double r2, double mj)
+{
+    const double y = rsqrt_seed(r2);
+    const double t = y * y;                 // exact: y has <= 24 significant bits... (<=53 anyway)
+    const double e = fma(-r2, t, 1.0);      // 1 - r2*y^2, |e| <~ 2^-20
+    const double my = mj * y;
+    const double y3m = my * t;              // m * y^3
+    const double p = fma(1.875, e, 1.5);    // 3/2 + 15/8 e
+    const double ye = y3m * e;
+    return fma(ye, p, y3m);                 // m*y^3*(1 + e*p)
+}
+
+struct DSArgs {
+    const double4 *src;       // sources, zero padded to a multiple of DS_TJ
+    const int *src_id;        // MASSLESS: particle id of each source; PAIRWISE: nullptr (id == j)
+    const double *src_altm;   // MASSLESS: mass used when the target is massless (m[rank] quirk)
+    int n_src;
+    const double4 *tgt;       // targets, indexed by particle id
+    int i_lo, i_hi;           // target range handled by this launch
+    double eps2, G;
+    double *acc;              // AoS [3n], indexed by particle id
+    double *partials;         // [grid][2][3][IB]
+    int NB, NT;               // target blocks, source tiles
+};
+
+template <int TI>
+struct Acc {
+    double x[TI], y[TI], z[TI];
+};
+
+// One shared-memory tile against the TI register-resident targets of this thread.
+//   CHECK   : mask j == i (self) and j >= n_src (padding); needed only where they can occur
+//   MASSLESS: per-target choice between the true source mass and the quirk mass
+template <int TI, bool CHECK, bool MASSLESS>
+__device__ __forceinline__ void tile_interactions(const double4 *__restrict__ tile, const int *__restrict__ tile_id,
+                                                  const double *__restrict__ tile_altm, int j_base, int n_src,
+                                                  const double (&xi)[TI], const double (&yi)[TI],
+                                                  const double (&zi)[TI], const int (&ii)[TI],
+                                                  const bool (&alt)[TI], double eps2, Acc<TI> &a)
+{
+#pragma unroll 4
+    for (int j = 0; j < DS_TJ; j++) {
+        const double4 pj = tile[j];
+        int jid = j_base + j;
+        double altm = 0.0;
+        if (MASSLESS) {
+            jid = tile_id[j];
+            altm = tile_altm[j];
+        }
+        const bool jvalid = (j_base + j) < n_src;
+#pragma unroll
+        for (int t = 0; t < TI; t++) {
+            const double dx = pj.x - xi[t];
+            const double dy = pj.y - yi[t];
+            const double dz = pj.z - zi[t];
+            double r2 = fma(dx, dx, eps2);
+            r2 = fma(dy, dy, r2);
+            r2 = fma(dz, dz, r2);
+            double mj = pj.w;
+            if (MASSLESS) mj = alt[t] ? altm : mj;
+            double s = inv_r3_times_m(r2, mj);
+            if (CHECK) {
+                if (jid == ii[t] || !jvalid) s = 0.0;
+            }
+            a.x[t] = fma(s, dx, a.x[t]);
+            a.y[t] = fma(s, dy, a.y[t]);
+            a.z[t] = fma(s, dz, a.z[t]);
+        }
+    }
+}
+
+__host__ __device__ inline long long unit_begin(long long c, long long U, long long C) { return (c * U) / C; }
+
+template <int TI, bool MASSLESS>
+__global__ void __launch_bounds__(DS_BLOCK, (TI <= 2 ? 4 : 2))
+direct_sum_kernel(const DSArgs p)
+{
+    constexpr int IB = DS_BLOCK * TI;
+    __shared__ double4 tile[DS_TJ];
+    __shared__ int tile_id[MASSLESS ? DS_TJ : 1];
+    __shared__ double tile_altm[MASSLESS ? DS_TJ : 1];
+
+    const int tid = threadIdx.x;
+    const long long U = (long long)p.NB * p.NT;
+    const long long C = gridDim.x;
+    const long long u0 = unit_begin(blockIdx.x, U, C);
+    const long long u1 = unit_begin(blockIdx.x + 1, U, C);
+    if (u0 >= u1) return;
+    const int ib_first = (int)(u0 / p.NT);
+
+    long long u = u0;
+    while (u < u1) {
+        const int ib = (int)(u / p.NT);
+        const int jt0 = (int)(u - (long long)ib * p.NT);
+        const long long seg_end = min(u1, (long long)(ib + 1) * p.NT);
+        const int jt1 = (int)(seg_end - (long long)ib * p.NT);
+        const bool full = (jt0 == 0 && jt1 == p.NT);
+
+        // targets of this thread
+        double xi[TI], yi[TI], zi[TI];
+        int ii[TI];
+        bool alt[TI];
+        Acc<TI> a;
+        const int blk_lo = p.i_lo + ib * IB;
+#pragma unroll
+        for (int t = 0; t < TI; t++) {
+            const int i = blk_lo + t * DS_BLOCK + tid;
+            ii[t] = i;
+            const double4 q = (i < p.i_hi) ? p.tgt[i] : make_double4(0.0, 0.0, 0.0, 1.0);
+            xi[t] = q.x; yi[t] = q.y; zi[t] = q.z;
+            alt[t] = MASSLESS ? (q.w == 0.0) : false;
+            a.x[t] = 0.0; a.y[t] = 0.0; a.z[t] = 0.0;
+        }
+        const int blk_hi = min(blk_lo + IB, p.i_hi);   // exclusive
+
+        // stream the tiles, prefetching the next one into registers while computing
+        double4 nxt = p.src[(size_t)jt0 * DS_TJ + tid];
+        int nxt_id = 0;
+        double nxt_altm = 0.0;
+        if (MASSLESS) {
+            nxt_id = p.src_id[(size_t)jt0 * DS_TJ + tid];
+            nxt_altm = p.src_altm[(size_t)jt0 * DS_TJ + tid];
+        }
+        for (int jt = jt0; jt < jt1; jt++) {
+            __syncthreads();
+            tile[tid] = nxt;
+            if (MASSLESS) { tile_id[tid] = nxt_id; tile_altm[tid] = nxt_altm; }
+            __syncthreads();
+            if (jt + 1 < jt1) {
+                nxt = p.src[(size_t)(jt + 1) * DS_TJ + tid];
+                if (MASSLESS) {
+                    nxt_id = p.src_id[(size_t)(jt + 1) * DS_TJ + tid];
+                    nxt_altm = p.src_altm[(size_t)(jt + 1) * DS_TJ + tid];
+                }
+            }
+            const int j_base = jt * DS_TJ;
+            bool need_check;
+            if (MASSLESS) need_check = true;
+            else need_check = (j_base + DS_TJ > p.n_src) || (j_base < blk_hi && j_base + DS_TJ > blk_lo);
+            if (need_check)
+                tile_interactions<TI, true, MASSLESS>(tile, tile_id, tile_altm, j_base, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
+            else
+                tile_interactions<TI, false, MASSLESS>(tile, tile_id, tile_altm, j_base, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
+        }
+
+        if (full) {
+#pragma unroll
+            for (int t = 0; t < TI; t++) {
+                const int i = ii[t];
+                if (i < p.i_hi) {
+                    // a_i = -G * sum (x_i - x_j) s = G * sum (x_j - x_i) s
+                    p.acc[3 * (size_t)i + 0] = p.G * a.x[t];
+                    p.acc[3 * (size_t)i + 1] = p.G * a.y[t];
+                    p.acc[3 * (size_t)i + 2] = p.G * a.z[t];
+                }
+            }
+        } else {
+            const int slot = (ib == ib_first) ? 0 : 1;
+            double *dst = p.partials + ((size_t)blockIdx.x * 2 + slot) * 3 * IB;
+#pragma unroll
+            for (int t = 0; t < TI; t++) {
+                const int li = t * DS_BLOCK + tid;
+                dst[0 * IB + li] = a.x[t];
+                dst[1 * IB + li] = a.y[t];
+                dst[2 * IB + li] = a.z[t];
+            }
+        }
+        u = seg_end;
+    }
+}
+
+// Adds the partial sums of every target block that was split over several CTAs, in CTA order.
+template <int TI>
+__global__ void __launch_bounds__(DS_BLOCK) direct_sum_fixup_kernel(const DSArgs p, int C)
+{
+    constexpr int IB = DS_BLOCK * TI;
+    const int ib = blockIdx.x;
+    const long long U = (long long)p.NB * p.NT;
+    const long long ua = (long long)ib * p.NT, ub = ua + p.NT - 1;
+    // owner(u) = largest c with unit_begin(c) <= u
+    auto owner = [&](long long u) {
+        int lo = 0, hi = C - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (unit_begin(mid, U, C) <= u) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    };
+    const int c_lo = owner(ua), c_hi = owner(ub);
+    if (c_lo == c_hi) return;   // one CTA had the whole block and wrote acc itself
+    for (int li = threadIdx.x; li < IB; li += DS_BLOCK) {
+        const int i = p.i_lo + ib * IB + li;
+        if (i >= p.i_hi) continue;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int c = c_lo; c <= c_hi; c++) {
+            const long long b = unit_begin(c, U, C), e = unit_begin(c + 1, U, C);
+            if (b >= e) continue;
+            const int slot = ((int)(b / p.NT) == ib) ? 0 : 1;
+            const double *src = p.partials + ((size_t)c * 2 + slot) * 3 * IB;
+            sx += src[0 * IB + li];
+            sy += src[1 * IB + li];
+            sz += src[2 * IB + li];
+        }
+        p.acc[3 * (size_t)i + 0] = p.G * sx;
+        p.acc[3 * (size_t)i + 1] = p.G * sy;
+        p.acc[3 * (size_t)i + 2] = p.G * sz;
+    }
+}
+
+template <int TI, bool MASSLESS>
+static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
+{
+    constexpr int IB = DS_BLOCK * TI;
+    const int n_tgt = a.i_hi - a.i_lo;
+    if (n_tgt <= 0 ) return GRAV_B200_OK;
+    a.NB = (n_tgt + IB - 1) / IB;
+    a.NT = (a.n_src + DS_TJ - 1) / DS_TJ;
+    if (a.NT == 0) {   // no sources at all: a = 0
+        GB_CUDA(cudaMemsetAsync(a.acc + 3 * (size_t)a.i_lo, 0, sizeof(double) * 3 * (size_t)n_tgt, c->stream));
+        return GRAV_B200_OK;
+    }
+    int occ = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, direct_sum_kernel<TI, MASSLESS>, DS_BLOCK, 0));
+    if (occ < 1) occ = 1;
+    const long long U = (long long)a.NB * a.NT;
+    long long grid = (long long)c->sm_count * occ;
+    if (grid > U) grid = U;
+    GB_TRY(c->partials.reserve((size_t)grid * 2 * 3 * IB * sizeof(double)));
+    a.partials = c->partials.as<double>();
+    direct_sum_kernel<TI, MASSLESS><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+    GB_LAUNCH_CHECK();
+    count_launch();
+    // a fix-up is needed iff some target block is split, i.e. unless every CTA boundary is a block boundary
+    bool split = false;
+    for (long long k = 1; k < grid && !split; k++) split = (unit_begin(k, U, grid) % a.NT) != 0;
+    if (split) {
+        direct_sum_fixup_kernel<TI><<<a.NB, DS_BLOCK, 0, c->stream>>>(a, (int)grid);
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
+    return GRAV_B200_OK;
+}
+
+static int ds_ti()
+{
+    static int ti = -1;
+    if (ti < 0) {
+        const char *e = getenv("GRAV_B200_DS_TI");
+        ti = (e && atoi(e) == 4) ? 4 : 2;
+    }
+    return ti;
+}
+
+int direct_sum_pairwise(grav_b200_ctx *c, double eps)
+{
+    DSArgs a{};
+    a.src = c->posm.as<double4>();
+    a.n_src = c->n;
+    a.tgt = c->posm.as<double4>();
+    a.i_lo = c->lo;
+    a.i_hi = c->hi;
+    a.eps2 = eps * eps;
+    a.G = c->G;
+    a.acc = c->acc.as<double>();
+    if (ds_ti() == 4) return launch_direct_sum<4, false>(c, a);
+    return launch_direct_sum<2, false>(c, a);
+}
+
+// ---- massless method ------------------------------------------------------------------
+// Reference semantics (src/acceleration.c:236-367): sources are the particles with m != 0, in
+// index order ("massive list").  A massive target feels every other massive particle with its
+// true mass.  A massless target feels massive particle number r of that list with mass m[r]
+// -- the reference indexes m by list rank, not by particle id (:357-359) -- reproduced here.
+__global__ void massless_flags_kernel(const double4 *__restrict__ posm, int n, int *__restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (posm[i].w != 0.0) ? 1 : 0;
+}
+
+__global__ void massless_compact_kernel(const double4 *__restrict__ posm, int n, const int *__restrict__ flag,
+                                        const int *__restrict__ rank, double4 *__restrict__ src,
+                                        int *__restrict__ src_id, double *__restrict__ src_altm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) {
+        const int r = rank[i];
+        src[r] = posm[i];
+        src_id[r] = i;
+        src_altm[r] = posm[r].w;   // m[rank]
+    }
+}
+
+int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);   // scan.cu
+
+int direct_sum_massless(grav_b200_ctx *c, double eps)
+{
+    const int n = c->n;
+    GB_TRY(c->stage_c.reserve(sizeof(int) * (size_t)(n + 1)));
+    GB_TRY(c->stage_d.reserve(sizeof(int) * (size_t)(n + 1)));
+    int *flag = c->stage_c.as<int>();
+    int *rank = c->stage_d.as<int>();
+    const int nb = (n + 255) / 256;
+    GB_CUDA(cudaMemsetAsync(flag + n, 0, sizeof(int), c->stream));
+    massless_flags_kernel<<<nb, 256, 0, c->stream>>>(c->posm.as<double4>(), n, flag);
+    GB_LAUNCH_CHECK();
+    count_launch();
+    GB_TRY(exclusive_scan_int(c, flag, rank, n + 1, c->misc));
+    int n_massive = 0;
+    GB_CUDA(cudaMemcpyAsync(&n_massive, rank + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    const int pad = ((n_massive + SRC_PAD - 1) / SRC_PAD) * SRC_PAD;
+    GB_TRY(c->msrc.reserve(sizeof(double4) * (size_t)(pad ? pad : SRC_PAD)));
+    GB_TRY(c->msrc_id.reserve(sizeof(int) * (size_t)(pad ? pad : SRC_PAD)));
+    GB_TRY(c->msrc_altm.reserve(sizeof(double) * (size_t)(pad ? pad : SRC_PAD)));
+    if (pad) {
+        GB_CUDA(cudaMemsetAsync(c->msrc.p, 0, sizeof(double4) * (size_t)pad, c->stream));
+        GB_CUDA(cudaMemsetAsync(c->msrc_id.p, 0xff, sizeof(int) * (size_t)pad, c->stream));
+        GB_CUDA(cudaMemsetAsync(c->msrc_altm.p, 0, sizeof(double) * (size_t)pad, c->stream));
+        massless_compact_kernel<<<nb, 256, 0, c->stream>>>(c->posm.as<double4>(), n, flag, rank, c->msrc.as<double4>(),
+                                                         c->msrc_id.as<int>(), c->msrc_altm.as<double>());
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
+    DSArgs a{};
+    a.src = c->msrc.as<double4>();
+    a.src_id = c->msrc_id.as<int>();
+    a.src_altm = c->msrc_altm.as<double>();
+    a.n_src = n_massive;
+    a.tgt = c->posm.as<double4>();
+    a.i_lo = c->lo;
+    a.i_hi = c->hi;
+    a.eps2 = eps * eps;
+    a.G = c->G;
+    a.acc = c->acc.as<double>();
+    return launch_direct_sum<2, true>(c, a);
+}
+
+}  // namespace gb

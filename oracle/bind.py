@@ -1,0 +1,252 @@
+"""ctypes bindings for the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs,
+never by the product package.  Two libraries:
+
+* ``oracle/libgrav_oracle.so``        our C restatement (grav_oracle.c)                     -> :class:`Oracle`
+* ``oracle/_ref/libgrav_sim_ref.so``  the UNMODIFIED reference compiled by oracle/Makefile  -> :class:`Reference`
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "libgrav_oracle.so"
+REF_SO = HERE / "_ref" / "libgrav_sim_ref.so"
+PROBE_SO = HERE / "_ref" / "libwhfast_probe.so"
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+i64p = C.POINTER(C.c_int64)
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def _f64(a, shape):
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
+
+
+def build(force=False):
+    """Compile the restatement (always possible: gcc only) and, where /root/reference exists, the reference."""
+    if force or not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < (HERE / "grav_oracle.c").stat().st_mtime:
+        subprocess.run(["make", "-C", str(HERE), "libgrav_oracle.so"], check=True, capture_output=True)
+    if not REF_SO.exists() and Path("/root/reference/src").is_dir():
+        subprocess.run(["make", "-C", str(HERE), "ref"], check=True, capture_output=True)
+
+
+class OracleTree(C.Structure):
+    _fields_ = [("box_width", C.c_double), ("n", C.c_int), ("num_nodes", C.c_int), ("keys", i64p), ("perm", ip),
+                ("num_particles", ip), ("num_children", ip), ("first_particle", ip), ("first_child", ip),
+                ("mass", dp), ("com_x", dp), ("com_y", dp), ("com_z", dp)]
+
+
+def _tree_dict(keys, perm, npart, nch, first, fc, mass, cx, cy, cz, n, M, box_width):
+    f = np.ctypeslib.as_array
+    return {"box_width": float(box_width), "num_nodes": int(M), "keys": f(keys, (n,)).copy(),
+            "sorted_indices": f(perm, (n,)).copy(), "num_particles": f(npart, (M,)).copy(),
+            "num_children": f(nch, (M,)).copy(), "first_particle": f(first, (M,)).copy(),
+            "first_child": f(fc, (M,)).copy(), "mass": f(mass, (M,)).copy(), "com_x": f(cx, (M,)).copy(),
+            "com_y": f(cy, (M,)).copy(), "com_z": f(cz, (M,)).copy()}
+
+
+class Oracle:
+    def __init__(self):
+        build()
+        L = self.L = C.CDLL(str(ORACLE_SO))
+        L.oracle_pairwise.argtypes = [dp, C.c_int, dp, dp, C.c_double, C.c_double]
+        L.oracle_pairwise.restype = None
+        L.oracle_massless.argtypes = L.oracle_pairwise.argtypes
+        L.oracle_whfast_pairwise.argtypes = [dp, C.c_int, dp, dp, C.c_double, dp, dp, C.c_double]
+        L.oracle_whfast_pairwise.restype = None
+        L.oracle_whfast_massless.argtypes = L.oracle_whfast_pairwise.argtypes
+        L.oracle_bounding_box.argtypes = [dp, dp, C.c_int, dp]
+        L.oracle_bounding_box.restype = None
+        L.oracle_morton_keys.argtypes = [i64p, C.c_int, dp, dp, C.c_double]
+        L.oracle_morton_keys.restype = None
+        L.oracle_sort_keys.argtypes = [i64p, ip, C.c_int]
+        L.oracle_build_tree.argtypes = [C.POINTER(OracleTree), C.c_int, dp, dp, C.c_int, dp, C.c_double]
+        L.oracle_free_tree.argtypes = [C.POINTER(OracleTree)]
+        L.oracle_free_tree.restype = None
+        L.oracle_barnes_hut.argtypes = [dp, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.oracle_energy.argtypes = [C.c_int, dp, dp, dp, C.c_double]
+        L.oracle_energy.restype = C.c_double
+
+    def acceleration(self, x, m, G, method="pairwise", softening_length=0.0, opening_angle=1.0,
+                     max_num_particles_per_leaf=1, fixed=False):
+        x = _f64(x, (-1, 3)); m = _f64(m, (-1,)); n = m.shape[0]
+        a = np.zeros_like(x)
+        if method == "pairwise":
+            self.L.oracle_pairwise(_d(a), n, _d(x), _d(m), G, softening_length)
+        elif method == "massless":
+            assert self.L.oracle_massless(_d(a), n, _d(x), _d(m), G, softening_length) == 0
+        elif method == "barnes_hut":
+            leaf = 1 if max_num_particles_per_leaf == -1 else max_num_particles_per_leaf
+            assert self.L.oracle_barnes_hut(_d(a), n, _d(x), _d(m), G, softening_length, opening_angle, leaf, int(fixed)) == 0
+        else:
+            raise ValueError(method)
+        return a
+
+    def whfast_acceleration(self, x, m, G, jacobi_x, eta, method="pairwise", softening_length=0.0, a0=None):
+        x = _f64(x, (-1, 3)); m = _f64(m, (-1,)); jx = _f64(jacobi_x, (-1, 3)); eta = _f64(eta, (-1,))
+        a = np.zeros_like(x) if a0 is None else _f64(a0, (-1, 3)).copy()
+        fn = self.L.oracle_whfast_pairwise if method == "pairwise" else self.L.oracle_whfast_massless
+        fn(_d(a), m.shape[0], _d(x), _d(m), G, _d(jx), _d(eta), softening_length)
+        return a
+
+    def morton_keys(self, x):
+        x = _f64(x, (-1, 3)); n = x.shape[0]
+        c = np.empty(3); w = np.empty(1)
+        self.L.oracle_bounding_box(_d(c), _d(w), n, _d(x))
+        keys = np.empty(n, dtype=np.int64)
+        self.L.oracle_morton_keys(keys.ctypes.data_as(i64p), n, _d(x), _d(c), float(w[0]))
+        return keys, c, float(w[0])
+
+    def construct_octree(self, x, m, max_num_particles_per_leaf=1, box_center=None, box_width=-1.0):
+        x = _f64(x, (-1, 3)); m = _f64(m, (-1,)); n = m.shape[0]
+        t = OracleTree()
+        bc = _d(_f64(box_center, (3,))) if box_center is not None else None
+        assert self.L.oracle_build_tree(C.byref(t), n, _d(x), _d(m), max_num_particles_per_leaf, bc, box_width) == 0
+        try:
+            return _tree_dict(t.keys, t.perm, t.num_particles, t.num_children, t.first_particle, t.first_child,
+                              t.mass, t.com_x, t.com_y, t.com_z, n, t.num_nodes, t.box_width)
+        finally:
+            self.L.oracle_free_tree(C.byref(t))
+
+    def energy(self, x, v, m, G):
+        x = _f64(x, (-1, 3)); v = _f64(v, (-1, 3)); m = _f64(m, (-1,))
+        return float(self.L.oracle_energy(m.shape[0], _d(x), _d(v), _d(m), G))
+
+
+# ---- the unmodified reference ---------------------------------------------------------------------------
+
+class RefErrorStatus(C.Structure):
+    _fields_ = [("return_code", C.c_int), ("traceback", C.c_char_p), ("traceback_code_", C.c_int)]
+
+
+class RefSystem(C.Structure):
+    _fields_ = [("num_particles", C.c_int), ("particle_ids", ip), ("x", dp), ("v", dp), ("m", dp), ("G", C.c_double)]
+
+
+class RefAccelerationParam(C.Structure):
+    _fields_ = [("method", C.c_int), ("opening_angle", C.c_double), ("softening_length", C.c_double),
+                ("max_num_particles_per_leaf", C.c_int)]
+
+
+class RefLinearOctree(C.Structure):
+    _fields_ = [("box_width", C.c_double), ("num_internal_nodes", C.c_int), ("keys", i64p), ("sorted_indices", ip),
+                ("tree_num_particles", ip), ("tree_num_internal_children", ip), ("tree_first_particle_sorted_idx", ip),
+                ("tree_first_internal_children_idx", ip), ("tree_mass", dp), ("com_x", dp), ("com_y", dp), ("com_z", dp)]
+
+
+METHODS = {"pairwise": 1, "massless": 2, "barnes_hut": 3}
+
+
+class Reference:
+    """The compiled upstream library, driven through its own public C API."""
+
+    @staticmethod
+    def available() -> bool:
+        build()
+        return REF_SO.exists()
+
+    def __init__(self, path: Path | None = None):
+        build()
+        L = self.L = C.CDLL(str(path or REF_SO))
+        L.acceleration.restype = RefErrorStatus
+        L.acceleration.argtypes = [dp, C.POINTER(RefSystem), C.POINTER(RefAccelerationParam)]
+        L.construct_octree.restype = RefErrorStatus
+        L.construct_octree.argtypes = [C.POINTER(RefLinearOctree), C.POINTER(RefSystem), C.POINTER(RefAccelerationParam), dp, C.c_double]
+        L.get_new_linear_octree.restype = RefLinearOctree
+        L.free_linear_octree.argtypes = [C.POINTER(RefLinearOctree)]
+        L.free_linear_octree.restype = None
+        L.compute_energy.restype = C.c_double
+        L.compute_energy.argtypes = [C.POINTER(RefSystem)]
+        L.load_built_in_system_python.argtypes = [C.c_char_p, ip, C.POINTER(ip), C.POINTER(dp), C.POINTER(dp), C.POINTER(dp), dp]
+
+    @staticmethod
+    def _sys(x, m, G, v=None):
+        s = RefSystem()
+        s.num_particles = m.shape[0]
+        s.particle_ids = None
+        s.x = _d(x); s.m = _d(m); s.v = _d(v) if v is not None else None
+        s.G = G
+        return s
+
+    @staticmethod
+    def _param(method, eps, theta, leaf):
+        p = RefAccelerationParam()
+        p.method = METHODS[method]; p.opening_angle = theta; p.softening_length = eps
+        p.max_num_particles_per_leaf = 1 if leaf == -1 else leaf
+        return p
+
+    def acceleration(self, x, m, G, method="pairwise", softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=1):
+        x = _f64(x, (-1, 3)); m = _f64(m, (-1,))
+        a = np.empty_like(x)
+        s = self._sys(x, m, G); p = self._param(method, softening_length, opening_angle, max_num_particles_per_leaf)
+        st = self.L.acceleration(_d(a), C.byref(s), C.byref(p))
+        if st.return_code != 0:
+            raise RuntimeError(f"reference error {st.return_code}: {st.traceback}")
+        return a
+
+    def construct_octree(self, x, m, max_num_particles_per_leaf=1, box_center=None, box_width=-1.0):
+        x = _f64(x, (-1, 3)); m = _f64(m, (-1,)); n = m.shape[0]
+        s = self._sys(x, m, 1.0); p = self._param("barnes_hut", 0.0, 1.0, max_num_particles_per_leaf)
+        t = self.L.get_new_linear_octree()
+        bc = _d(_f64(box_center, (3,))) if box_center is not None else None
+        st = self.L.construct_octree(C.byref(t), C.byref(s), C.byref(p), bc, box_width)
+        if st.return_code != 0:
+            raise RuntimeError(f"reference error {st.return_code}: {st.traceback}")
+        try:
+            d = _tree_dict(t.keys, t.sorted_indices, t.tree_num_particles, t.tree_num_internal_children,
+                           t.tree_first_particle_sorted_idx, t.tree_first_internal_children_idx, t.tree_mass,
+                           t.com_x, t.com_y, t.com_z, n, t.num_internal_nodes, t.box_width)
+        finally:
+            self.L.free_linear_octree(C.byref(t))
+        d["first_child"] = np.where(d["num_children"] > 0, d["first_child"], -1)   # uninitialised for leaves upstream
+        return d
+
+    def energy(self, x, v, m, G):
+        x = _f64(x, (-1, 3)); v = _f64(v, (-1, 3)); m = _f64(m, (-1,))
+        s = self._sys(x, m, G, v)
+        return float(self.L.compute_energy(C.byref(s)))
+
+    def whfast_acceleration(self, x, m, G, jacobi_x, eta, method="pairwise", softening_length=0.0, a0=None):
+        """The reference's static whfast_acceleration(), reached through oracle/ref_whfast_probe.c."""
+        if not hasattr(self, "P"):
+            self.P = C.CDLL(str(PROBE_SO))
+            self.P.probe_whfast_acceleration.argtypes = [dp, C.c_int, dp, dp, C.c_double, dp, dp, C.c_int, C.c_double]
+        x = _f64(x, (-1, 3)); m = _f64(m, (-1,)); jx = _f64(jacobi_x, (-1, 3)); eta = _f64(eta, (-1,))
+        a = np.zeros_like(x) if a0 is None else _f64(a0, (-1, 3)).copy()
+        rc = self.P.probe_whfast_acceleration(_d(a), m.shape[0], _d(x), _d(m), G, _d(jx), _d(eta), METHODS[method], softening_length)
+        if rc != 0:
+            raise RuntimeError(f"reference whfast_acceleration -> {rc}")
+        return a
+
+    def built_in_system(self, name: str):
+        n = C.c_int(); ids = ip(); x = dp(); v = dp(); m = dp(); G = C.c_double()
+        rc = self.L.load_built_in_system_python(name.encode(), C.byref(n), C.byref(ids), C.byref(x), C.byref(v), C.byref(m), C.byref(G))
+        if rc != 0:
+            raise RuntimeError(f"load_built_in_system_python({name}) -> {rc}")
+        f = np.ctypeslib.as_array
+        return f(x, (n.value, 3)).copy(), f(v, (n.value, 3)).copy(), f(m, (n.value,)).copy(), G.value
+
+
+def jacobi_inputs(x, m):
+    """eta (prefix masses, src/integrator_whfast.c:1266-1279) and Jacobi positions (cartesian_to_jacobi, :682-727
+    restated with numpy) -- the extra inputs of the WHFast acceleration kernels."""
+    x = _f64(x, (-1, 3)); m = _f64(m, (-1,))
+    eta = np.cumsum(m)
+    n = m.shape[0]
+    jx = np.zeros_like(x)
+    xcm = m[0] * x[0]
+    for i in range(1, n):
+        jx[i] = x[i] - xcm / eta[i - 1]
+        xcm = xcm * (1.0 + m[i] / eta[i - 1]) + m[i] * jx[i]
+    jx[0] = xcm / eta[n - 1]
+    return jx, eta

@@ -1,0 +1,62 @@
+/*
+ * grav_oracle.h -- CPU restatement of grav_sim's acceleration hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product (libgrav_b200.so, libgrav_sim_b200.so) never links or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function here against
+ * the unmodified reference compiled to oracle/_ref/libgrav_sim_ref.so (bit-exact for keys,
+ * permutation, node arrays, moments and BH accelerations; bit-exact for the pairwise / massless /
+ * WHFast sums, which use the reference's summation order), and tests/golden/ holds vectors minted
+ * from that reference build by tests/golden/make_golden.py.
+ *
+ * Every function cites the reference lines it restates (paths relative to the upstream tree).
+ * Compile with -ffp-contract=off: the reference is built without FMA contraction
+ * (CMakeLists.txt:56-61: -O3, no -march, no -ffast-math).
+ */
+#ifndef GRAV_ORACLE_H
+#define GRAV_ORACLE_H
+#include <stdint.h>
+
+/* src/acceleration.c:177-234 */
+void oracle_pairwise(double *a, int n, const double *x, const double *m, double G, double eps);
+/* src/acceleration.c:236-367 (with the m[rank] indexing of :357-359) */
+int oracle_massless(double *a, int n, const double *x, const double *m, double G, double eps);
+/* src/integrator_whfast.c:839-957 and :959-1264; aux[] defined as zero-initialised */
+void oracle_whfast_pairwise(double *a, int n, const double *x, const double *m, double G,
+                            const double *jacobi_x, const double *eta, double eps);
+int oracle_whfast_massless(double *a, int n, const double *x, const double *m, double G,
+                           const double *jacobi_x, const double *eta, double eps);
+
+/* src/linear_octree.c:113-146 */
+void oracle_bounding_box(double center[3], double *width, int n, const double *x);
+/* src/linear_octree.c:159-202 */
+void oracle_morton_keys(int64_t *keys, int n, const double *x, const double center[3], double width);
+/* src/linear_octree.c:216-326: result == stable sort by key; keys permuted in place, perm out */
+int oracle_sort_keys(int64_t *keys, int *perm, int n);
+
+typedef struct OracleTree {
+    double box_width;
+    int n, num_nodes;
+    int64_t *keys;   /* sorted */
+    int *perm;       /* sorted_indices */
+    int *num_particles, *num_children, *first_particle, *first_child; /* first_child = -1 for leaves */
+    double *mass, *com_x, *com_y, *com_z;
+} OracleTree;
+
+/* src/linear_octree.c:406-576, 590-736, 825-962, restated level-by-level.
+ * box_center NULL or box_width <= 0: automatic bounding box. Returns 0, or -1 on allocation failure. */
+int oracle_build_tree(OracleTree *t, int n, const double *x, const double *m, int max_leaf,
+                      const double *box_center, double box_width);
+void oracle_free_tree(OracleTree *t);
+
+/* src/acceleration_barnes_hut.c:78-248.  fixed_mode 0 = bug-for-bug, 1 = corrected walk. */
+void oracle_bh_walk(double *a, const OracleTree *t, const double *x, const double *m, double G,
+                    double eps, double theta, int fixed_mode);
+/* src/acceleration_barnes_hut.c:33-76 */
+int oracle_barnes_hut(double *a, int n, const double *x, const double *m, double G, double eps,
+                      double theta, int max_leaf, int fixed_mode);
+
+/* src/utils.c:27-59 */
+double oracle_energy(int n, const double *x, const double *v, const double *m, double G);
+#endif

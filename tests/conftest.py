@@ -1,0 +1,72 @@
+import importlib.util
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def load_package():
+    """Import gravity-simulator_b200/ (hyphenated directory) as module `gravity_simulator_b200`."""
+    name = "gravity_simulator_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg = ROOT / "gravity-simulator_b200"
+    spec = importlib.util.spec_from_file_location(name, pkg / "__init__.py", submodule_search_locations=[str(pkg)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def gb():
+    return load_package()
+
+
+@pytest.fixture(scope="session")
+def ics(gb):
+    import importlib
+    return importlib.import_module("gravity_simulator_b200.ics")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle.bind import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def reference():
+    from oracle.bind import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libgrav_sim_ref.so not built (needs /root/reference at build time)")
+    return Reference()
+
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+
+    def load(name):
+        return np.load(GOLDEN / f"{name}.npz")
+    return load
+
+
+def max_rel_err(a, ref):
+    """max_i |a_i - ref_i|_2 / |ref_i|_2 (SURVEY.md section 8d parity gate)."""
+    import numpy as np
+    num = np.linalg.norm(a - ref, axis=1)
+    den = np.linalg.norm(ref, axis=1)
+    den = np.where(den > 0, den, 1.0)
+    return float(np.max(num / den))

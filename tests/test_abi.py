@@ -1,0 +1,87 @@
+"""CPU tests: the C-ABI libraries load and export every symbol the headers declare; host-side validation
+logic of the shim behaves like the reference; compute entries fail loudly without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols(header: Path, pattern: str):
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    return sorted(set(re.findall(pattern, text)))
+
+
+def test_abi_header_symbols_exported(gb):
+    abi, shim = gb.load()
+    names = declared_symbols(ROOT / "include" / "grav_b200.h", r"\b(grav_b200_[a-z0-9_]+)\s*\(")
+    assert set(names) == set(gb.ABI_SYMBOLS), set(names) ^ set(gb.ABI_SYMBOLS)
+    for n in names:
+        assert hasattr(abi, n), n
+
+
+def test_shim_exports_reference_symbols(gb):
+    _, shim = gb.load()
+    for n in gb.SHIM_SYMBOLS:
+        assert hasattr(shim, n), n
+
+
+def test_struct_layouts_match_reference_abi(gb):
+    # x86-64 SysV layouts of the reference structs
+    assert C.sizeof(gb.AccelerationParam) == 32
+    assert gb.AccelerationParam.opening_angle.offset == 8 and gb.AccelerationParam.max_num_particles_per_leaf.offset == 24
+    assert C.sizeof(gb.ErrorStatus) == 24
+    assert C.sizeof(gb.System) == 48 and gb.System.G.offset == 40
+    assert C.sizeof(gb.LinearOctree) == 96
+
+
+def test_param_defaults_and_validation(gb):
+    _, shim = gb.load()
+    p = shim.get_new_acceleration_param()
+    assert (p.method, p.opening_angle, p.softening_length, p.max_num_particles_per_leaf) == (1, 1.0, 0.0, -1)
+    p = gb.make_param("barnes_hut")
+    assert p.max_num_particles_per_leaf == 1          # -1 -> 1 for Barnes-Hut only
+    assert gb.make_param("pairwise").max_num_particles_per_leaf == -1
+    for kw, msg in [(dict(method=7), "Unknown acceleration method"),
+                    (dict(method="pairwise", softening_length=-1.0), "Softening length is negative"),
+                    (dict(method="barnes_hut", opening_angle=-0.5), "Opening angle is negative"),
+                    (dict(method="barnes_hut", max_num_particles_per_leaf=0), "must be positive")]:
+        with pytest.raises(gb.GravB200Error, match=msg):
+            gb.make_param(**kw)
+    # a negative opening angle is only an error for Barnes-Hut (src/acceleration.c:97-108)
+    gb.make_param("pairwise", opening_angle=-1.0)
+
+
+def test_unknown_method_in_dispatch(gb):
+    _, shim = gb.load()
+    x = np.zeros((2, 3)); m = np.ones(2); a = np.zeros((2, 3))
+    s = gb.make_system(x, m, 1.0)
+    p = gb.make_param("pairwise")
+    p.method = 42
+    st = shim.acceleration(a.ctypes.data_as(gb.c_double_p), C.byref(s), C.byref(p))
+    assert st.return_code == 2 and "Unknown acceleration method. Got: 42" in gb.take_traceback(st)
+
+
+def test_check_if_included(gb):
+    _, shim = gb.load()
+    a = 0b101_011_000 << (3 * 18)
+    b = 0b101_011_111 << (3 * 18)
+    assert shim.linear_octree_check_if_included(a, b, 2) and not shim.linear_octree_check_if_included(a, b, 3)
+    assert shim.linear_octree_check_if_included(a, b, 0)
+
+
+def test_no_cpu_fallback(gb):
+    """Without a GPU every compute entry must fail loudly (GRAV_FAILURE + device message), never compute on the host."""
+    if gb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    x = np.random.default_rng(0).normal(size=(16, 3)); m = np.ones(16)
+    for method in ("pairwise", "massless", "barnes_hut"):
+        with pytest.raises(gb.GravB200Error, match="no CUDA device|CUDA error"):
+            gb.acceleration(x, m, 1.0, method)
+    with pytest.raises(gb.GravB200Error):
+        gb.Context()
+    with pytest.raises(gb.GravB200Error):
+        gb.construct_octree(x, m)

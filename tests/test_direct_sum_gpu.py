@@ -1,0 +1,99 @@
+"""GPU parity: the sm_100a direct-sum kernels, called through the drop-in `acceleration()` C symbol, against
+the golden vectors of the unmodified reference and against the CPU oracle on fresh seeded inputs.
+
+Tolerance (BASELINE.json north_star / SURVEY.md section 8d): max_i |a_gpu - a_ref|_2 / |a_ref|_2 <= 1e-12.
+The GPU evaluates every ordered interaction row-wise with FMA; the reference walks unordered pairs with
+Newton-3 updates, so only the summation order and rounding differ."""
+import numpy as np
+import pytest
+
+from conftest import max_rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("case", ["solar_forces", "plummer2048", "uniform1500", "clustered1024", "massless600",
+                                  "tiny1", "tiny2", "tiny3"])
+def test_pairwise_matches_golden(gb, golden, case):
+    g = golden(case)
+    a = gb.acceleration(g["x"], g["m"], float(g["G"]), "pairwise", float(g["eps"]))
+    assert max_rel_err(a, g["a_pairwise"]) <= TOL
+
+
+@pytest.mark.parametrize("case", ["solar_forces", "massless600", "tiny1", "tiny2", "tiny3"])
+def test_massless_matches_golden(gb, golden, case):
+    g = golden(case)
+    a = gb.acceleration(g["x"], g["m"], float(g["G"]), "massless", float(g["eps"]))
+    assert max_rel_err(a, g["a_massless"]) <= TOL
+
+
+@pytest.mark.parametrize("n,eps", [(255, 0.0), (256, 0.0), (257, 0.01), (511, 0.0), (513, 0.0), (1000, 0.0), (4099, 0.02),
+                                   (16384, 0.01)])
+def test_pairwise_vs_oracle_sizes(gb, oracle, ics, n, eps):
+    """Ragged sizes around the tile (256) and target-block (512) boundaries; config 2 (Plummer N=16384, softened)."""
+    x, v, m, G = ics.plummer(n, seed=n)
+    m = m * np.random.default_rng(n).uniform(0.5, 1.5, n)   # unequal masses
+    a = gb.acceleration(x, m, G, "pairwise", eps)
+    ref = oracle.acceleration(x, m, G, "pairwise", eps)
+    assert max_rel_err(a, ref) <= TOL
+
+
+def test_massless_vs_oracle_belt(gb, oracle, ics):
+    """Config 3 shape: 9 massive + many massless (asteroid belt), plus shuffled massive ids for the m[rank] quirk."""
+    xs, vs, ms, G = ics.solar_system()
+    rng = np.random.default_rng(3)
+    k = 20000
+    r = rng.uniform(2.0, 3.35, k); ph = rng.uniform(0, 2 * np.pi, k)
+    belt = np.stack([r * np.cos(ph), r * np.sin(ph), rng.normal(0, 0.1, k)], axis=1)
+    x = np.concatenate([xs, belt]); m = np.concatenate([ms, np.zeros(k)])
+    a = gb.acceleration(x, m, G, "massless", 0.0)
+    assert max_rel_err(a, oracle.acceleration(x, m, G, "massless", 0.0)) <= TOL
+    perm = rng.permutation(x.shape[0])
+    a = gb.acceleration(x[perm], m[perm], G, "massless", 0.0)
+    assert max_rel_err(a, oracle.acceleration(x[perm], m[perm], G, "massless", 0.0)) <= TOL
+
+
+def test_massless_equals_pairwise_when_all_massive(gb, ics):
+    x, v, m, G = ics.plummer(3000, seed=5)
+    a1 = gb.acceleration(x, m, G, "pairwise", 0.01)
+    a2 = gb.acceleration(x, m, G, "massless", 0.01)
+    assert max_rel_err(a2, a1) <= 1e-14
+
+
+def test_coincident_particles_give_nan_like_reference(gb, oracle):
+    """eps = 0 with two particles at the same point: the reference returns NaN for both (G/0 * 0); so do we,
+    while every other particle stays finite and correct."""
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(700, 3)); x[17] = x[400]
+    m = rng.random(700) + 0.1
+    a = gb.acceleration(x, m, 1.0, "pairwise", 0.0)
+    ref = oracle.acceleration(x, m, 1.0, "pairwise", 0.0)
+    assert np.isnan(a[17]).all() and np.isnan(a[400]).all() and np.isnan(ref[17]).all()
+    ok = np.ones(700, bool); ok[[17, 400]] = False
+    assert max_rel_err(a[ok], ref[ok]) <= TOL
+
+
+def test_full_size_properties(gb, ics):
+    """BASELINE size (N = 2^20 is the bench; 2^17 here keeps the test quick): size-independent properties.
+    Newton-3: sum_i m_i a_i = 0 to rounding; determinism: two runs are bit-identical (no FP atomics);
+    linearity in G and in the masses."""
+    n = 1 << 17
+    x, v, m, G = ics.plummer(n, seed=21)
+    a = gb.acceleration(x, m, G, "pairwise", 0.01)
+    mom = (m[:, None] * a).sum(0)
+    assert np.abs(mom).max() <= 1e-12 * np.abs(m[:, None] * a).sum()
+    a2 = gb.acceleration(x, m, G, "pairwise", 0.01)
+    assert np.array_equal(a, a2)
+    a3 = gb.acceleration(x, 2.0 * m, 0.5 * G, "pairwise", 0.01)
+    assert max_rel_err(a3, a) <= 1e-15
+
+
+def test_context_resident_matches_one_shot(gb, ics):
+    x, v, m, G = ics.uniform_cube(5000, seed=8)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.acceleration("pairwise", 0.0)
+        a = c.accelerations()
+        assert np.array_equal(c.positions(), x)
+    assert np.array_equal(a, gb.acceleration(x, m, G, "pairwise", 0.0))

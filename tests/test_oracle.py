@@ -1,0 +1,99 @@
+"""CPU tests: the oracle restatement (oracle/grav_oracle.c) against the golden vectors minted from the
+unmodified reference, and -- where oracle/_ref is present -- against the reference library itself."""
+import numpy as np
+import pytest
+
+from conftest import max_rel_err
+
+TREE_KEYS = ["keys", "sorted_indices", "num_particles", "num_children", "first_particle", "first_child", "mass",
+             "com_x", "com_y", "com_z"]
+FORCE_CASES = ["solar_forces", "plummer2048", "uniform1500", "clustered1024", "massless600", "tiny1", "tiny2", "tiny3"]
+
+
+def parse_bh(key):
+    # a_bh_t0.5_l1
+    _, _, t, l = key.split("_")
+    return float(t[1:]), int(l[1:])
+
+
+@pytest.mark.parametrize("case", FORCE_CASES)
+def test_oracle_matches_golden_forces(oracle, golden, case):
+    g = golden(case)
+    x, m, G, eps = g["x"], g["m"], float(g["G"]), float(g["eps"])
+    for key in g.files:
+        if key == "a_pairwise":
+            a = oracle.acceleration(x, m, G, "pairwise", eps)
+        elif key == "a_massless":
+            a = oracle.acceleration(x, m, G, "massless", eps)
+        elif key.startswith("a_bh_"):
+            theta, leaf = parse_bh(key)
+            a = oracle.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
+        else:
+            continue
+        # same operations in the same order as the reference: bit-exact
+        assert np.array_equal(a, g[key], equal_nan=True), (case, key, max_rel_err(a, g[key]))
+
+
+@pytest.mark.parametrize("case", ["solar_forces", "plummer2048", "uniform1500", "clustered1024", "tiny1", "tiny2", "tiny3"])
+def test_oracle_matches_golden_trees(oracle, golden, case):
+    g = golden(case)
+    leaves = sorted({int(k.split("_")[1][1:]) for k in g.files if k.startswith("tree_l")})
+    assert leaves
+    for leaf in leaves:
+        t = oracle.construct_octree(g["x"], g["m"], leaf)
+        assert t["num_nodes"] == int(g[f"tree_l{leaf}_num_nodes"])
+        assert t["box_width"] == float(g[f"tree_l{leaf}_box_width"])
+        for k in TREE_KEYS:
+            assert np.array_equal(t[k], g[f"tree_l{leaf}_{k}"], equal_nan=True), (case, leaf, k)
+
+
+def test_oracle_matches_golden_whfast(oracle, golden):
+    for case in ("whfast_belt", "whfast_solar"):
+        g = golden(case)
+        for key in g.files:
+            if not key.startswith("a_whfast_"):
+                continue
+            method = key.split("_")[2]
+            eps = float(key.split("eps")[1])
+            a = oracle.whfast_acceleration(g["x"], g["m"], float(g["G"]), g["jacobi_x"], g["eta"], method, eps)
+            assert np.array_equal(a, g[key], equal_nan=True), (case, key, max_rel_err(a[1:], g[key][1:]))
+
+
+def test_oracle_vs_reference_live(oracle, reference, ics):
+    """Fresh inputs not in the golden set (bigger, other seeds); needs the compiled reference."""
+    for name, (x, v, m, G) in {"uniform": ics.uniform_cube(5000, 11), "plummer": ics.plummer(6000, 12),
+                               "clustered": ics.clustered(3000, 13)}.items():
+        for leaf in (1, 3):
+            to, tr = oracle.construct_octree(x, m, leaf), reference.construct_octree(x, m, leaf)
+            assert to["num_nodes"] == tr["num_nodes"] and to["box_width"] == tr["box_width"]
+            for k in TREE_KEYS:
+                assert np.array_equal(to[k], tr[k], equal_nan=True), (name, leaf, k)
+        for theta in (0.3, 0.5, 1.0):
+            ao = oracle.acceleration(x, m, G, "barnes_hut", 0.01, theta, 1)
+            ar = reference.acceleration(x, m, G, "barnes_hut", 0.01, theta, 1)
+            assert np.array_equal(ao, ar, equal_nan=True), (name, theta)
+        assert np.array_equal(oracle.acceleration(x, m, G, "pairwise", 0.0), reference.acceleration(x, m, G, "pairwise", 0.0),
+                              equal_nan=True)   # exact duplicates with eps = 0 give NaN in both
+        assert oracle.energy(x, v, m, G) == reference.energy(x, v, m, G)
+
+
+def test_known_answer_invariants(oracle, golden):
+    """Invariants the reference itself obeys: theta=0 BH == pairwise to rounding,
+    Newton-3 momentum conservation, massless == pairwise when no mass is zero."""
+    g = golden("uniform1500")
+    x, m, G = g["x"], g["m"], float(g["G"])
+    ap = oracle.acceleration(x, m, G, "pairwise", 0.0)
+    assert max_rel_err(g["a_bh_t0.0_l1"], ap) < 1e-12
+    assert np.abs((m[:, None] * ap).sum(0)).max() < 1e-13 * np.abs(m[:, None] * ap).sum()
+    assert np.array_equal(oracle.acceleration(x, m, G, "massless", 0.0), ap)
+
+
+def test_fixed_mode_is_more_accurate(oracle, golden):
+    """The opt-in corrected walk is a real improvement over the reference semantics."""
+    g = golden("plummer2048")
+    x, m, G, eps = g["x"], g["m"], float(g["G"]), float(g["eps"])
+    exact = g["a_pairwise"]
+    ref_mode = g["a_bh_t0.5_l1"]
+    fixed = oracle.acceleration(x, m, G, "barnes_hut", eps, 0.5, 1, fixed=True)
+    err = lambda a: np.mean(np.linalg.norm(a - exact, axis=1) / np.linalg.norm(exact, axis=1))
+    assert err(fixed) < 0.02 < err(ref_mode)

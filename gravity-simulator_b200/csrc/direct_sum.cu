@@ -40,8 +40,11 @@ __device__ __forceinline__ double inv_r3_times_m(double r2, double mj)
     const double my = mj * y;
     const double y3m = my * t;              // m * y^3
     const double p = fma(1.875, e, 1.5);    // 3/2 + 15/8 e
-    const double ye = y3m * e;
-    return fma(ye, p, y3m);                 // m*y^3*(1 + e*p)
+    const double q = e * p;
+    // m*y^3*(1 + q).  Written so the DFMA has only two distinct register sources: on sm_100 a
+    // DFMA with three distinct register operands occupies the FP64 pipe for 3 cycles instead of 2
+    // (measured, scratch/fp64_micro.cu; DESIGN.md "FP64 pipe").
+    return fma(q, y3m, y3m);
 }
 
 struct DSArgs {
@@ -72,7 +75,7 @@ __device__ __forceinline__ void tile_interactions(const double4 *__restrict__ ti
                                                   const double (&zi)[TI], const int (&ii)[TI],
                                                   const bool (&alt)[TI], double eps2, Acc<TI> &a)
 {
-#pragma unroll 4
+#pragma unroll 2
     for (int j = 0; j < DS_TJ; j++) {
         const double4 pj = tile[j];
         int jid = j_base + j;
@@ -105,8 +108,19 @@ __device__ __forceinline__ void tile_interactions(const double4 *__restrict__ ti
 
 __host__ __device__ inline long long unit_begin(long long c, long long U, long long C) { return (c * U) / C; }
 
-template <int TI, bool MASSLESS>
-__global__ void __launch_bounds__(DS_BLOCK, (TI <= 2 ? 4 : 2))
+// A source tile needs the checked loop when it can contain the self term (it overlaps the target block)
+// or padding (it is the last, partial tile).
+__device__ __forceinline__ bool tile_is_special(int jt, int n_src, int blk_lo, int blk_hi)
+{
+    const int j_base = jt * DS_TJ;
+    return (j_base + DS_TJ > n_src) || (j_base < blk_hi && j_base + DS_TJ > blk_lo);
+}
+
+// Main kernel.  CHECK=false: the fast loop only; special tiles are SKIPPED (direct_sum_special_kernel adds
+// them afterwards), which keeps this kernel's code identical to the tuned loop (one inner-loop variant, no
+// extra live registers).  CHECK=true: every tile goes through the checked loop (small problems, massless).
+template <int TI, bool CHECK, bool MASSLESS>
+__global__ void __launch_bounds__(DS_BLOCK, 2)   // tuned on B200: TI=4, 2 CTAs/SM, unroll 2 (scratch/ds_tune.cu)
 direct_sum_kernel(const DSArgs p)
 {
     constexpr int IB = DS_BLOCK * TI;
@@ -147,34 +161,17 @@ direct_sum_kernel(const DSArgs p)
         }
         const int blk_hi = min(blk_lo + IB, p.i_hi);   // exclusive
 
-        // stream the tiles, prefetching the next one into registers while computing
-        double4 nxt = p.src[(size_t)jt0 * DS_TJ + tid];
-        int nxt_id = 0;
-        double nxt_altm = 0.0;
-        if (MASSLESS) {
-            nxt_id = p.src_id[(size_t)jt0 * DS_TJ + tid];
-            nxt_altm = p.src_altm[(size_t)jt0 * DS_TJ + tid];
-        }
+        // stream the source tiles through shared memory (the second CTA of the SM computes meanwhile)
         for (int jt = jt0; jt < jt1; jt++) {
+            if (!CHECK && tile_is_special(jt, p.n_src, blk_lo, blk_hi)) continue;   // block-uniform
             __syncthreads();
-            tile[tid] = nxt;
-            if (MASSLESS) { tile_id[tid] = nxt_id; tile_altm[tid] = nxt_altm; }
-            __syncthreads();
-            if (jt + 1 < jt1) {
-                nxt = p.src[(size_t)(jt + 1) * DS_TJ + tid];
-                if (MASSLESS) {
-                    nxt_id = p.src_id[(size_t)(jt + 1) * DS_TJ + tid];
-                    nxt_altm = p.src_altm[(size_t)(jt + 1) * DS_TJ + tid];
-                }
+            tile[tid] = p.src[(size_t)jt * DS_TJ + tid];
+            if (MASSLESS) {
+                tile_id[tid] = p.src_id[(size_t)jt * DS_TJ + tid];
+                tile_altm[tid] = p.src_altm[(size_t)jt * DS_TJ + tid];
             }
-            const int j_base = jt * DS_TJ;
-            bool need_check;
-            if (MASSLESS) need_check = true;
-            else need_check = (j_base + DS_TJ > p.n_src) || (j_base < blk_hi && j_base + DS_TJ > blk_lo);
-            if (need_check)
-                tile_interactions<TI, true, MASSLESS>(tile, tile_id, tile_altm, j_base, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
-            else
-                tile_interactions<TI, false, MASSLESS>(tile, tile_id, tile_altm, j_base, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
+            __syncthreads();
+            tile_interactions<TI, CHECK, MASSLESS>(tile, tile_id, tile_altm, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
         }
 
         if (full) {
@@ -200,6 +197,51 @@ direct_sum_kernel(const DSArgs p)
             }
         }
         u = seg_end;
+    }
+}
+
+// The tiles the fast kernel skipped: for each target block, the (at most IB/DS_TJ + 1) source tiles that
+// overlap it plus the partial last tile, through the checked loop; acc += G * sum.  One CTA per block,
+// runs after the main kernel and its fix-up (same stream), so the result is deterministic.
+template <int TI>
+__global__ void __launch_bounds__(DS_BLOCK, 2) direct_sum_special_kernel(const DSArgs p)
+{
+    constexpr int IB = DS_BLOCK * TI;
+    __shared__ double4 tile[DS_TJ];
+    const int tid = threadIdx.x, ib = blockIdx.x;
+    double xi[TI], yi[TI], zi[TI];
+    int ii[TI];
+    bool alt[TI];
+    Acc<TI> a;
+    const int blk_lo = p.i_lo + ib * IB;
+#pragma unroll
+    for (int t = 0; t < TI; t++) {
+        const int i = blk_lo + t * DS_BLOCK + tid;
+        ii[t] = i;
+        const double4 q = (i < p.i_hi) ? p.tgt[i] : make_double4(0.0, 0.0, 0.0, 1.0);
+        xi[t] = q.x; yi[t] = q.y; zi[t] = q.z;
+        alt[t] = false;
+        a.x[t] = 0.0; a.y[t] = 0.0; a.z[t] = 0.0;
+    }
+    const int blk_hi = min(blk_lo + IB, p.i_hi);
+    const int jt_a = blk_lo / DS_TJ, jt_b = min((blk_hi - 1) / DS_TJ, p.NT - 1);
+    const int last = p.NT - 1;
+    const bool last_partial = (p.n_src % DS_TJ) != 0 && last > jt_b;
+    for (int k = jt_a; k <= jt_b + (last_partial ? 1 : 0); k++) {
+        const int jt = (k <= jt_b) ? k : last;
+        __syncthreads();
+        tile[tid] = p.src[(size_t)jt * DS_TJ + tid];
+        __syncthreads();
+        tile_interactions<TI, true, false>(tile, nullptr, nullptr, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
+    }
+#pragma unroll
+    for (int t = 0; t < TI; t++) {
+        const int i = ii[t];
+        if (i < p.i_hi) {
+            p.acc[3 * (size_t)i + 0] += p.G * a.x[t];
+            p.acc[3 * (size_t)i + 1] += p.G * a.y[t];
+            p.acc[3 * (size_t)i + 2] += p.G * a.z[t];
+        }
     }
 }
 
@@ -241,27 +283,31 @@ __global__ void __launch_bounds__(DS_BLOCK) direct_sum_fixup_kernel(const DSArgs
     }
 }
 
-template <int TI, bool MASSLESS>
+constexpr int DS_TI = 4;
+
+template <bool MASSLESS>
 static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
 {
+    constexpr int TI = DS_TI;
     constexpr int IB = DS_BLOCK * TI;
     const int n_tgt = a.i_hi - a.i_lo;
-    if (n_tgt <= 0 ) return GRAV_B200_OK;
+    if (n_tgt <= 0) return GRAV_B200_OK;
     a.NB = (n_tgt + IB - 1) / IB;
     a.NT = (a.n_src + DS_TJ - 1) / DS_TJ;
     if (a.NT == 0) {   // no sources at all: a = 0
         GB_CUDA(cudaMemsetAsync(a.acc + 3 * (size_t)a.i_lo, 0, sizeof(double) * 3 * (size_t)n_tgt, c->stream));
         return GRAV_B200_OK;
     }
-    int occ = 0;
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, direct_sum_kernel<TI, MASSLESS>, DS_BLOCK, 0));
-    if (occ < 1) occ = 1;
+    // Small source counts (and the massless method) run everything through the checked loop in one kernel;
+    // otherwise fast kernel + special-tile kernel.
+    const bool all_checked = MASSLESS || a.NT <= 64;
     const long long U = (long long)a.NB * a.NT;
-    long long grid = (long long)c->sm_count * occ;
+    long long grid = (long long)c->sm_count * 2;
     if (grid > U) grid = U;
     GB_TRY(c->partials.reserve((size_t)grid * 2 * 3 * IB * sizeof(double)));
     a.partials = c->partials.as<double>();
-    direct_sum_kernel<TI, MASSLESS><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+    if (all_checked) direct_sum_kernel<TI, true, MASSLESS><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+    else direct_sum_kernel<TI, false, false><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
     GB_LAUNCH_CHECK();
     count_launch();
     // a fix-up is needed iff some target block is split, i.e. unless every CTA boundary is a block boundary
@@ -272,17 +318,12 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
         GB_LAUNCH_CHECK();
         count_launch();
     }
-    return GRAV_B200_OK;
-}
-
-static int ds_ti()
-{
-    static int ti = -1;
-    if (ti < 0) {
-        const char *e = getenv("GRAV_B200_DS_TI");
-        ti = (e && atoi(e) == 4) ? 4 : 2;
+    if (!all_checked) {
+        direct_sum_special_kernel<TI><<<a.NB, DS_BLOCK, 0, c->stream>>>(a);
+        GB_LAUNCH_CHECK();
+        count_launch();
     }
-    return ti;
+    return GRAV_B200_OK;
 }
 
 int direct_sum_pairwise(grav_b200_ctx *c, double eps)
@@ -296,8 +337,7 @@ int direct_sum_pairwise(grav_b200_ctx *c, double eps)
     a.eps2 = eps * eps;
     a.G = c->G;
     a.acc = c->acc.as<double>();
-    if (ds_ti() == 4) return launch_direct_sum<4, false>(c, a);
-    return launch_direct_sum<2, false>(c, a);
+    return launch_direct_sum<false>(c, a);
 }
 
 // ---- massless method ------------------------------------------------------------------
@@ -366,7 +406,7 @@ int direct_sum_massless(grav_b200_ctx *c, double eps)
     a.eps2 = eps * eps;
     a.G = c->G;
     a.acc = c->acc.as<double>();
-    return launch_direct_sum<2, true>(c, a);
+    return launch_direct_sum<true>(c, a);
 }
 
 }  // namespace gb

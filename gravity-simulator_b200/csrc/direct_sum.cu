@@ -65,8 +65,26 @@ struct Acc {
     double x[TI], y[TI], z[TI];
 };
 
+// One ordered interaction target <- source (16 FP64-pipe instructions in the unchecked form).
+//   CHECK: mask the self term (source id == target id) and padding sources.
+template <bool CHECK>
+__device__ __forceinline__ void interaction(const double4 pj, double mj, bool masked, double xi, double yi, double zi,
+                                            double eps2, double &ax, double &ay, double &az)
+{
+    const double dx = pj.x - xi, dy = pj.y - yi, dz = pj.z - zi;
+    double r2 = fma(dx, dx, eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    double s = inv_r3_times_m(r2, mj);
+    if (CHECK) {
+        if (masked) s = 0.0;
+    }
+    ax = fma(s, dx, ax);
+    ay = fma(s, dy, ay);
+    az = fma(s, dz, az);
+}
+
 // One shared-memory tile against the TI register-resident targets of this thread.
-//   CHECK   : mask j == i (self) and j >= n_src (padding); needed only where they can occur
 //   MASSLESS: per-target choice between the true source mass and the quirk mass
 template <int TI, bool CHECK, bool MASSLESS>
 __device__ __forceinline__ void tile_interactions(const double4 *__restrict__ tile, const int *__restrict__ tile_id,
@@ -84,24 +102,12 @@ __device__ __forceinline__ void tile_interactions(const double4 *__restrict__ ti
             jid = tile_id[j];
             altm = tile_altm[j];
         }
-        const bool jvalid = (j_base + j) < n_src;
+        const bool jpad = CHECK && (j_base + j) >= n_src;
 #pragma unroll
         for (int t = 0; t < TI; t++) {
-            const double dx = pj.x - xi[t];
-            const double dy = pj.y - yi[t];
-            const double dz = pj.z - zi[t];
-            double r2 = fma(dx, dx, eps2);
-            r2 = fma(dy, dy, r2);
-            r2 = fma(dz, dz, r2);
             double mj = pj.w;
             if (MASSLESS) mj = alt[t] ? altm : mj;
-            double s = inv_r3_times_m(r2, mj);
-            if (CHECK) {
-                if (jid == ii[t] || !jvalid) s = 0.0;
-            }
-            a.x[t] = fma(s, dx, a.x[t]);
-            a.y[t] = fma(s, dy, a.y[t]);
-            a.z[t] = fma(s, dz, a.z[t]);
+            interaction<CHECK>(pj, mj, CHECK && (jpad || jid == ii[t]), xi[t], yi[t], zi[t], eps2, a.x[t], a.y[t], a.z[t]);
         }
     }
 }

@@ -1,0 +1,448 @@
+// Barnes-Hut stages BH-4..BH-5 on the device: linear-octree construction with the reference's node
+// numbering, and the mass / centre-of-mass moments.
+//
+// Reference: setup_node + binary_search_num_particles_per_octant + helper_construct_octree
+// (src/linear_octree.c:342-393, 406-576, 590-823), a serial depth-first walk that hands out node ids as
+// nodes are expanded.  Here the same tree is produced level by level (validated bit-exact against the
+// reference through oracle/grav_oracle.c, which restates this algorithm on the CPU):
+//
+//   discovery   breadth-first.  The root is always expanded.  The children of an expanded node of level
+//               l-1 are the maximal runs of equal (key >> 3(21-l)) in its sorted range; a child is
+//               expanded iff it holds more than max_leaf particles and l < 21.  One thread per expanded
+//               node finds the (at most 8) run boundaries by binary search; the next level's records are
+//               placed with a prefix sum, so record order is deterministic (by start position).
+//   numbering   the reference serves expanded nodes in (start position, level) order and gives each all of
+//               its children at once, so   first_child(u) = 1 + P[s_u] + same_start(u)   where P is the
+//               exclusive prefix sum over sorted positions of "children created by expanded nodes starting
+//               here" and same_start(u) counts the children of u's expanded ancestors that start at s_u.
+//               id(child k of u) = first_child(u) + k.
+//   moments     levels deepest-first, one thread per expanded node, children in id order; a leaf child adds
+//               its particles one at a time in sorted order, an expanded child adds its finished sums;
+//               separate multiply and add (no FMA) and IEEE division, as the reference's x86-64 build
+//               does.  Leaves keep mass = com = 0 (src/linear_octree.c:567-570).
+#include "internal.cuh"
+
+namespace gb {
+
+constexpr int MAX_LEVEL = 21;
+
+struct ExpRec {       // one expanded (= has children) node, 64 bytes
+    int b[9];         // child k covers sorted positions [b[k], b[k+1]); before expansion b[0] = s, b[1] = e
+    int level;        // level of this node; its children are level + 1
+    int parent;       // index of the parent record, -1 for the root
+    int rank;         // position among the parent's children
+    int same_start;   // children of expanded ancestors that start at the same position
+    int nch;
+    int first_child;  // node id of child 0
+    int id;           // node id of this node
+};
+static_assert(sizeof(ExpRec) == 64, "ExpRec layout");
+
+struct WalkNode {     // what the tree walk reads per node, 64 bytes
+    double mass, cx, cy, cz;
+    long long kq;     // key the inclusion test compares against (mode dependent)
+    int first, count, nch, fc;
+    long long pad;
+};
+static_assert(sizeof(WalkNode) == 64, "WalkNode layout");
+
+int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);
+int bh_keys(grav_b200_ctx *c, const double *box_center, double box_width, bool want_unsorted);
+int radix_sort_pairs(grav_b200_ctx *c);
+
+__global__ void root_init_kernel(ExpRec *rec, int n)
+{
+    ExpRec r;
+    for (int k = 0; k < 9; k++) r.b[k] = 0;
+    r.b[0] = 0; r.b[1] = n;
+    r.level = 0; r.parent = -1; r.rank = 0; r.same_start = 0; r.nch = 0; r.first_child = 1; r.id = 0;
+    rec[0] = r;
+}
+
+// first position q in (p, e) whose level prefix differs from that of p (keys are sorted => it is larger)
+__device__ __forceinline__ int run_end(const long long *__restrict__ K, int p, int e, int shift)
+{
+    const long long v = K[p] >> shift;
+    if (e - p <= 16) {
+        int q = p + 1;
+        while (q < e && (K[q] >> shift) == v) q++;
+        return q;
+    }
+    int lo = p + 1, hi = e;   // answer in [lo, hi]
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if ((K[mid] >> shift) == v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) expand_kernel(ExpRec *__restrict__ rec, int begin, int count,
+                                                    const long long *__restrict__ K, int max_leaf,
+                                                    int *__restrict__ W, int *__restrict__ nexp)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) {
+        if (t == count) nexp[t] = 0;   // sentinel so the scan also yields the total
+        return;
+    }
+    ExpRec r = rec[begin + t];
+    const int s = r.b[0], e = r.b[1];
+    const int l = r.level + 1, shift = 3 * (MAX_LEVEL - l);
+    int nch = 0, grow = 0;
+    int p = s;
+    while (p < e) {
+        const int q = run_end(K, p, e, shift);
+        r.b[nch] = p;
+        nch++;
+        if (q - p > max_leaf && l < MAX_LEVEL) grow++;
+        p = q;
+    }
+    r.b[nch] = e;
+    for (int k = nch + 1; k < 9; k++) r.b[k] = e;
+    r.nch = nch;
+    rec[begin + t] = r;
+    nexp[t] = grow;
+    atomicAdd(&W[s], nch);
+}
+
+__global__ void __launch_bounds__(128) emit_kernel(ExpRec *__restrict__ rec, int begin, int count, int next_begin,
+                                                  const int *__restrict__ off, int max_leaf)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const ExpRec r = rec[begin + t];
+    const int l = r.level + 1;
+    if (l >= MAX_LEVEL) return;
+    int o = next_begin + off[t];
+    for (int k = 0; k < r.nch; k++) {
+        const int cs = r.b[k], ce = r.b[k + 1];
+        if (ce - cs > max_leaf) {
+            ExpRec c;
+            for (int j = 0; j < 9; j++) c.b[j] = 0;
+            c.b[0] = cs; c.b[1] = ce;
+            c.level = l; c.parent = begin + t; c.rank = k;
+            c.same_start = (cs == r.b[0]) ? r.same_start + r.nch : 0;
+            c.nch = 0; c.first_child = 0; c.id = 0;
+            rec[o++] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) first_child_kernel(ExpRec *__restrict__ rec, int ne, const int *__restrict__ P)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < ne) rec[u].first_child = 1 + P[rec[u].b[0]] + rec[u].same_start;
+}
+
+__global__ void __launch_bounds__(256) fill_children_kernel(const ExpRec *__restrict__ rec, int ne, int *__restrict__ np,
+                                                           int *__restrict__ nchild, int *__restrict__ first,
+                                                           int *__restrict__ fc)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= ne) return;
+    const ExpRec r = rec[u];
+    for (int k = 0; k < r.nch; k++) {
+        const int id = r.first_child + k;
+        np[id] = r.b[k + 1] - r.b[k];
+        first[id] = r.b[k];
+        nchild[id] = 0;    // leaf unless fill_own_kernel says otherwise
+        fc[id] = -1;       // the reference leaves this uninitialised for leaves
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_own_kernel(ExpRec *__restrict__ rec, int ne, int n, int *__restrict__ np,
+                                                      int *__restrict__ nchild, int *__restrict__ first,
+                                                      int *__restrict__ fc)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= ne) return;
+    ExpRec r = rec[u];
+    const int id = (r.parent < 0) ? 0 : rec[r.parent].first_child + r.rank;
+    rec[u].id = id;
+    nchild[id] = r.nch;
+    fc[id] = r.first_child;
+    if (r.parent < 0) { np[0] = n; first[0] = 0; }
+}
+
+__global__ void __launch_bounds__(128) moments_kernel(const ExpRec *__restrict__ rec, int begin, int count,
+                                                     const int *__restrict__ perm, const double4 *__restrict__ posm,
+                                                     const int *__restrict__ nchild, double *__restrict__ mass,
+                                                     double *__restrict__ mtd, double *__restrict__ cx,
+                                                     double *__restrict__ cy, double *__restrict__ cz)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const ExpRec r = rec[begin + t];
+    double tot = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int k = 0; k < r.nch; k++) {
+        const int cid = r.first_child + k;
+        if (nchild[cid] == 0) {
+            for (int p = r.b[k]; p < r.b[k + 1]; p++) {
+                const double4 q = posm[perm[p]];
+                tot = __dadd_rn(tot, q.w);
+                sx = __dadd_rn(sx, __dmul_rn(q.w, q.x));
+                sy = __dadd_rn(sy, __dmul_rn(q.w, q.y));
+                sz = __dadd_rn(sz, __dmul_rn(q.w, q.z));
+            }
+        } else {
+            tot = __dadd_rn(tot, mass[cid]);
+            sx = __dadd_rn(sx, mtd[3 * (size_t)cid + 0]);
+            sy = __dadd_rn(sy, mtd[3 * (size_t)cid + 1]);
+            sz = __dadd_rn(sz, mtd[3 * (size_t)cid + 2]);
+        }
+    }
+    const int id = r.id;
+    mass[id] = tot;
+    mtd[3 * (size_t)id + 0] = sx; mtd[3 * (size_t)id + 1] = sy; mtd[3 * (size_t)id + 2] = sz;
+    cx[id] = __ddiv_rn(sx, tot); cy[id] = __ddiv_rn(sy, tot); cz[id] = __ddiv_rn(sz, tot);
+}
+
+// Packed per-node record for the walk.  Reference mode reproduces the walk's key fetch
+// keys[sorted_indices[first_particle]] -- the SORTED key array indexed by an ORIGINAL particle id
+// (src/acceleration_barnes_hut.c:143-147); fixed mode uses the node's own first key.
+__global__ void __launch_bounds__(256) walk_nodes_kernel(int M, const int *__restrict__ np, const int *__restrict__ nchild,
+                                                        const int *__restrict__ first, const int *__restrict__ fc,
+                                                        const double *__restrict__ mass, const double *__restrict__ cx,
+                                                        const double *__restrict__ cy, const double *__restrict__ cz,
+                                                        const long long *__restrict__ K, const int *__restrict__ perm,
+                                                        int fixed_mode, WalkNode *__restrict__ out)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= M) return;
+    WalkNode w;
+    w.mass = mass[id]; w.cx = cx[id]; w.cy = cy[id]; w.cz = cz[id];
+    w.first = first[id]; w.count = np[id]; w.nch = nchild[id]; w.fc = fc[id];
+    w.kq = fixed_mode ? K[w.first] : K[perm[w.first]];
+    w.pad = 0;
+    out[id] = w;
+}
+
+static int grow_preserve(grav_b200_ctx *c, DevBuf &buf, size_t used_bytes, size_t need_bytes)
+{
+    if (need_bytes <= buf.cap && buf.p) return GRAV_B200_OK;
+    size_t want = need_bytes + need_bytes / 2;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = need_bytes;
+        e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    }
+    if (buf.p && used_bytes) {
+        e = cudaMemcpyAsync(np, buf.p, used_bytes, cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { cudaFree(np); return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__); }
+    }
+    if (buf.p) cudaFree(buf.p);
+    buf.p = np;
+    buf.cap = want;
+    return GRAV_B200_OK;
+}
+
+// Builds keys, permutation, node arrays and moments on the device.  Leaves c->tree ready for bh_walk().
+int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double box_width)
+{
+    DevTree &t = c->tree;
+    const int n = c->n;
+    stage_begin(c, ST_MORTON);
+    GB_TRY(bh_keys(c, box_center, box_width, false));
+    stage_end(c, ST_MORTON);
+    stage_begin(c, ST_SORT);
+    GB_TRY(radix_sort_pairs(c));
+    stage_end(c, ST_SORT);
+
+    stage_begin(c, ST_BUILD);
+    const long long *K = t.keys.as<long long>();
+    GB_TRY(t.wsum.reserve(sizeof(int) * ((size_t)n + 1)));
+    GB_TRY(t.wscan.reserve(sizeof(int) * ((size_t)n + 1)));
+    GB_CUDA(cudaMemsetAsync(t.wsum.p, 0, sizeof(int) * ((size_t)n + 1), c->stream));
+    // a generous first guess for the record count; grown on demand (deep chains can exceed it)
+    GB_TRY(grow_preserve(c, t.exp_rec, 0, sizeof(ExpRec) * ((size_t)n / 2 + 1024)));
+    root_init_kernel<<<1, 1, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), n);
+    GB_LAUNCH_CHECK();
+    count_launch();
+
+    int level_off[MAX_LEVEL + 2];
+    level_off[0] = 0;
+    level_off[1] = 1;
+    int levels = 1;   // number of levels holding expanded nodes
+    for (int l = 0; l < MAX_LEVEL; l++) {
+        const int begin = level_off[l], count = level_off[l + 1] - begin;
+        GB_TRY(t.counters.reserve(sizeof(int) * ((size_t)count + 1)));
+        int *nexp = t.counters.as<int>();
+        expand_kernel<<<(count + 1 + 127) / 128, 128, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, K, max_leaf,
+                                                                     t.wsum.as<int>(), nexp);
+        GB_LAUNCH_CHECK();
+        count_launch();
+        if (l + 1 >= MAX_LEVEL) { levels = l + 1; break; }   // level-21 nodes are never expanded
+        GB_TRY(exclusive_scan_int(c, nexp, nexp, count + 1, t.scan_tmp));
+        int total = 0;
+        GB_CUDA(cudaMemcpyAsync(&total, nexp + count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        levels = l + 1;
+        if (total == 0) break;
+        const size_t used = sizeof(ExpRec) * (size_t)level_off[l + 1];
+        GB_TRY(grow_preserve(c, t.exp_rec, used, used + sizeof(ExpRec) * (size_t)total));
+        emit_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, level_off[l + 1], nexp,
+                                                               max_leaf);
+        GB_LAUNCH_CHECK();
+        count_launch();
+        level_off[l + 2] = level_off[l + 1] + total;
+    }
+    const int ne = level_off[levels];
+    t.num_expanded = ne;
+    t.max_level = levels;
+
+    // numbering
+    GB_TRY(exclusive_scan_int(c, t.wsum.as<int>(), t.wscan.as<int>(), n + 1, t.scan_tmp));
+    int total_children = 0;
+    GB_CUDA(cudaMemcpyAsync(&total_children, t.wscan.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaMemcpyAsync(&t.box_width, t.bbox.as<double>() + 8 + 3, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    const int M = 1 + total_children;
+    t.num_nodes = M;
+    const size_t mi = sizeof(int) * (size_t)M, md = sizeof(double) * (size_t)M;
+    GB_TRY(t.node_np.reserve(mi));
+    GB_TRY(t.node_nch.reserve(mi));
+    GB_TRY(t.node_first.reserve(mi));
+    GB_TRY(t.node_fc.reserve(mi));
+    GB_TRY(t.node_mass.reserve(md));
+    GB_TRY(t.node_cx.reserve(md));
+    GB_TRY(t.node_cy.reserve(md));
+    GB_TRY(t.node_cz.reserve(md));
+    GB_TRY(t.node_mtd.reserve(3 * md));
+    GB_CUDA(cudaMemsetAsync(t.node_mass.p, 0, md, c->stream));
+    GB_CUDA(cudaMemsetAsync(t.node_cx.p, 0, md, c->stream));
+    GB_CUDA(cudaMemsetAsync(t.node_cy.p, 0, md, c->stream));
+    GB_CUDA(cudaMemsetAsync(t.node_cz.p, 0, md, c->stream));
+    ExpRec *rec = t.exp_rec.as<ExpRec>();
+    const int eb = (ne + 255) / 256;
+    first_child_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, t.wscan.as<int>());
+    GB_LAUNCH_CHECK();
+    fill_children_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
+                                                   t.node_fc.as<int>());
+    GB_LAUNCH_CHECK();
+    fill_own_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, n, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
+                                              t.node_fc.as<int>());
+    GB_LAUNCH_CHECK();
+    count_launch(3);
+
+    // moments, deepest level first
+    for (int l = levels - 1; l >= 0; l--) {
+        const int begin = level_off[l], count = level_off[l + 1] - begin;
+        if (count <= 0) continue;
+        moments_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(rec, begin, count, t.perm.as<int>(), c->posm.as<double4>(),
+                                                                  t.node_nch.as<int>(), t.node_mass.as<double>(),
+                                                                  t.node_mtd.as<double>(), t.node_cx.as<double>(),
+                                                                  t.node_cy.as<double>(), t.node_cz.as<double>());
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
+    stage_end(c, ST_BUILD);
+    return GRAV_B200_OK;
+}
+
+int bh_pack_walk_nodes(grav_b200_ctx *c)
+{
+    DevTree &t = c->tree;
+    const int M = t.num_nodes;
+    GB_TRY(t.node_walk.reserve(sizeof(WalkNode) * (size_t)M));
+    walk_nodes_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(M, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
+                                                            t.node_fc.as<int>(), t.node_mass.as<double>(), t.node_cx.as<double>(),
+                                                            t.node_cy.as<double>(), t.node_cz.as<double>(), t.keys.as<long long>(),
+                                                            t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0,
+                                                            t.node_walk.as<WalkNode>());
+    GB_LAUNCH_CHECK();
+    count_launch();
+    return GRAV_B200_OK;
+}
+
+}  // namespace gb
+
+// ---- host-pointer entries for stage-level parity tests and the construct_octree() drop-in ---------------
+using namespace gb;
+
+namespace gb {
+int default_ctx_locked_begin(grav_b200_ctx **out);   // context.cu: takes the one-shot mutex
+void default_ctx_locked_end();
+}
+
+template <class T>
+static int copy_out(grav_b200_ctx *c, T **dst, const void *d_src, size_t count)
+{
+    *dst = (T *)malloc(sizeof(T) * (count ? count : 1));
+    if (!*dst) { set_error("malloc failed for %zu bytes", sizeof(T) * count); return GRAV_B200_ENOMEM; }
+    GB_CUDA(cudaMemcpyAsync(*dst, d_src, sizeof(T) * count, cudaMemcpyDeviceToHost, c->stream));
+    return GRAV_B200_OK;
+}
+
+extern "C" int grav_b200_construct_octree(int n, const double *x, const double *m, int max_leaf, const double *box_center,
+                                          double box_width, double *out_box_width, int *out_num_nodes, int64_t **keys,
+                                          int **sorted_indices, int **tree_num_particles, int **tree_num_internal_children,
+                                          int **tree_first_particle_sorted_idx, int **tree_first_internal_children_idx,
+                                          double **tree_mass, double **tree_com_x, double **tree_com_y, double **tree_com_z)
+{
+    if (!x || !m || !out_box_width || !out_num_nodes || !keys || !sorted_indices || !tree_num_particles ||
+        !tree_num_internal_children || !tree_first_particle_sorted_idx || !tree_first_internal_children_idx || !tree_mass ||
+        !tree_com_x || !tree_com_y || !tree_com_z) {
+        set_error("NULL pointer argument");
+        return GRAV_B200_EINVAL;
+    }
+    if (n < 1) { set_error("num_particles must be >= 1, got %d", n); return GRAV_B200_EINVAL; }
+    if (max_leaf == -1) max_leaf = 1;
+    if (max_leaf < 1) { set_error("Maximum number of particles per leaf must be positive. Got: %d", max_leaf); return GRAV_B200_EINVAL; }
+    grav_b200_ctx *c;
+    GB_TRY(default_ctx_locked_begin(&c));
+    int rc = grav_b200_ctx_set_system(c, n, x, nullptr, m, 1.0);
+    if (rc == GRAV_B200_OK) rc = bh_build(c, max_leaf, box_center, box_width);
+    if (rc == GRAV_B200_OK) {
+        DevTree &t = c->tree;
+        const size_t M = (size_t)t.num_nodes;
+        *out_box_width = t.box_width;
+        *out_num_nodes = t.num_nodes;
+        rc = copy_out(c, keys, t.keys.p, (size_t)n);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, sorted_indices, t.perm.p, (size_t)n);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_num_particles, t.node_np.p, M);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_num_internal_children, t.node_nch.p, M);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_first_particle_sorted_idx, t.node_first.p, M);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_first_internal_children_idx, t.node_fc.p, M);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_mass, t.node_mass.p, M);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_x, t.node_cx.p, M);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_y, t.node_cy.p, M);
+        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_z, t.node_cz.p, M);
+        if (rc == GRAV_B200_OK) {
+            cudaError_t e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+        }
+    }
+    default_ctx_locked_end();
+    return rc;
+}
+
+extern "C" int grav_b200_morton_keys(int n, const double *x, int64_t *keys_unsorted, double *out_center, double *out_width)
+{
+    if (!x || !keys_unsorted) { set_error("NULL pointer argument"); return GRAV_B200_EINVAL; }
+    if (n < 1) { set_error("num_particles must be >= 1, got %d", n); return GRAV_B200_EINVAL; }
+    grav_b200_ctx *c;
+    GB_TRY(default_ctx_locked_begin(&c));
+    // masses are irrelevant for keys: reuse x's first n values as a stand-in to avoid an extra host buffer
+    double *ones = (double *)calloc((size_t)n, sizeof(double));
+    int rc = ones ? GRAV_B200_OK : GRAV_B200_ENOMEM;
+    if (rc == GRAV_B200_OK) rc = grav_b200_ctx_set_system(c, n, x, nullptr, ones, 1.0);
+    if (rc == GRAV_B200_OK) rc = bh_keys(c, nullptr, -1.0, true);
+    if (rc == GRAV_B200_OK) {
+        cudaError_t e = cudaMemcpyAsync(keys_unsorted, c->tree.keys_unsorted.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        double box[4];
+        if (e == cudaSuccess) e = cudaMemcpyAsync(box, c->tree.bbox.as<double>() + 8, sizeof(box), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "morton_keys copy-out", __FILE__, __LINE__);
+        else {
+            if (out_center) { out_center[0] = box[0]; out_center[1] = box[1]; out_center[2] = box[2]; }
+            if (out_width) *out_width = box[3];
+        }
+    }
+    free(ones);
+    default_ctx_locked_end();
+    return rc;
+}

@@ -132,6 +132,15 @@ static int default_ctx(grav_b200_ctx **out)
     return GRAV_B200_OK;
 }
 
+int default_ctx_locked_begin(grav_b200_ctx **out)
+{
+    g_mu.lock();
+    const int rc = default_ctx(out);
+    if (rc != GRAV_B200_OK) g_mu.unlock();
+    return rc;
+}
+void default_ctx_locked_end() { g_mu.unlock(); }
+
 static int check_sys(const void *a, int n, const void *x, const void *m)
 {
     if (!a || !x || !m) { set_error("NULL array pointer"); return GRAV_B200_EINVAL; }

@@ -3,13 +3,9 @@
 namespace gb {
 static int nyi(const char *w) { set_error("%s: not implemented yet", w); return GRAV_B200_ECUDA; }
 int whfast_accel(grav_b200_ctx *, const double *, const double *, double, bool) { return nyi("whfast_accel"); }
-int bh_build(grav_b200_ctx *, int, const double *, double) { return nyi("bh_build"); }
-int bh_walk(grav_b200_ctx *, double, double) { return nyi("bh_walk"); }
 }
 using namespace gb;
 extern "C" {
-int grav_b200_construct_octree(int, const double *, const double *, int, const double *, double, double *, int *, int64_t **, int **, int **, int **, int **, int **, double **, double **, double **, double **) { return nyi("construct_octree"); }
-int grav_b200_morton_keys(int, const double *, int64_t *, double *, double *) { return nyi("morton_keys"); }
 int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *, int, double, double, int) { return nyi("leapfrog_begin"); }
 int grav_b200_ctx_leapfrog_steps(grav_b200_ctx *, double, int64_t) { return nyi("leapfrog_steps"); }
 int grav_b200_ctx_energy(grav_b200_ctx *, double *) { return nyi("energy"); }

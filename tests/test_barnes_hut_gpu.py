@@ -1,0 +1,132 @@
+"""GPU parity for the Barnes-Hut path, through the drop-in `construct_octree()` / `acceleration()` symbols.
+
+Bars (BASELINE.json north_star): Morton keys, sort permutation and octree node layout bit-exact; moments
+bit-exact (ordered non-contracted sums); reference-mode accelerations compared with the reference's own output
+-- the walk reproduces the per-particle depth-first order with IEEE operations, so we assert bit equality,
+which is stronger than the 1e-12 the spec asks for."""
+import numpy as np
+import pytest
+
+from conftest import max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+TREE_KEYS = ["keys", "sorted_indices", "num_particles", "num_children", "first_particle", "first_child", "mass",
+             "com_x", "com_y", "com_z"]
+CASES = ["solar_forces", "plummer2048", "uniform1500", "clustered1024", "tiny1", "tiny2", "tiny3"]
+
+
+def assert_tree_equal(t, ref, ctx=""):
+    assert t["num_nodes"] == ref["num_nodes"], ctx
+    assert t["box_width"] == ref["box_width"], ctx
+    for k in TREE_KEYS:
+        assert np.array_equal(t[k], ref[k], equal_nan=True), (ctx, k)
+
+
+def golden_tree(g, leaf):
+    d = {k: g[f"tree_l{leaf}_{k}"] for k in TREE_KEYS}
+    d["num_nodes"] = int(g[f"tree_l{leaf}_num_nodes"])
+    d["box_width"] = float(g[f"tree_l{leaf}_box_width"])
+    return d
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tree_matches_golden(gb, golden, case):
+    g = golden(case)
+    for leaf in sorted({int(k.split("_")[1][1:]) for k in g.files if k.startswith("tree_l")}):
+        assert_tree_equal(gb.construct_octree(g["x"], g["m"], leaf), golden_tree(g, leaf), f"{case} leaf={leaf}")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_bh_acceleration_matches_golden(gb, golden, case):
+    g = golden(case)
+    keys = [k for k in g.files if k.startswith("a_bh_")]
+    assert keys
+    for key in keys:
+        _, _, t, l = key.split("_")
+        a = gb.acceleration(g["x"], g["m"], float(g["G"]), "barnes_hut", float(g["eps"]), float(t[1:]), int(l[1:]))
+        assert np.array_equal(a, g[key], equal_nan=True), (case, key, max_rel_err(a, g[key]))
+
+
+def test_morton_keys_stage(gb, oracle, ics):
+    for x in (ics.uniform_cube(10000, 3)[0], ics.plummer(7777, 4)[0], ics.clustered(3000, 5)[0], np.zeros((5, 3)),
+              np.array([[1.0, 2.0, 3.0]])):
+        k, c, w = gb.morton_keys(x)
+        ko, co, wo = oracle.morton_keys(x)
+        assert np.array_equal(k, ko) and np.array_equal(c, co, equal_nan=True) and (w == wo)
+    # the particle on the max edge of the widest axis wraps to cell 0 on that axis (reference quirk)
+    x = ics.uniform_cube(1000, 6)[0]
+    k, c, w = gb.morton_keys(x)
+    widest = np.argmax(x.max(0) - x.min(0))
+    i = np.argmax(x[:, widest])
+    assert (k[i] >> widest) & 0x1249249249249249 == 0
+
+
+@pytest.mark.parametrize("n,leaf", [(1 << 15, 1), (50000, 2), (1 << 17, 1), (100003, 8)])
+def test_tree_vs_oracle_large(gb, oracle, ics, n, leaf):
+    for name, (x, v, m, G) in {"plummer": ics.plummer(n, n), "uniform": ics.uniform_cube(n, n + 1)}.items():
+        m = m * np.random.default_rng(n).uniform(0.5, 1.5, n)
+        assert_tree_equal(gb.construct_octree(x, m, leaf), oracle.construct_octree(x, m, leaf), f"{name} n={n} leaf={leaf}")
+
+
+def test_tree_vs_oracle_clustered_and_fixed_box(gb, oracle, ics):
+    x, v, m, G = ics.clustered(20000, 17)
+    for leaf in (1, 4):
+        assert_tree_equal(gb.construct_octree(x, m, leaf), oracle.construct_octree(x, m, leaf), f"clustered leaf={leaf}")
+    # caller-supplied box (construct_octree's box_center / box_width arguments, src/linear_octree.c:856-867)
+    x, v, m, G = ics.uniform_cube(5000, 2)
+    c, w = np.array([0.1, -0.2, 0.05]), 2.5
+    assert_tree_equal(gb.construct_octree(x, m, 1, c, w), oracle.construct_octree(x, m, 1, c, w), "fixed box")
+
+
+@pytest.mark.parametrize("n,theta,eps,leaf", [(20000, 0.5, 0.0, 1), (30000, 1.0, 0.01, 1), (16384, 0.3, 0.01, 4), (60000, 0.5, 0.0, 1)])
+def test_bh_acceleration_vs_oracle(gb, oracle, ics, n, theta, eps, leaf):
+    """Includes config 4 (two-Plummer galaxy collision, N=60000, theta=0.5, eps=0)."""
+    x, v, m, G = ics.two_plummer(n // 2, seed=n) if n == 60000 else ics.plummer(n, seed=n)
+    a = gb.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
+    ref = oracle.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
+    assert np.array_equal(a, ref, equal_nan=True), max_rel_err(a, ref)
+
+
+def test_bh_theta_zero_equals_direct_sum(gb, ics):
+    x, v, m, G = ics.uniform_cube(4000, 9)
+    a_bh = gb.acceleration(x, m, G, "barnes_hut", 0.0, 0.0, 1)
+    a_ds = gb.acceleration(x, m, G, "pairwise", 0.0)
+    assert max_rel_err(a_bh, a_ds) < 1e-12
+
+
+def test_bh_fixed_mode(gb, oracle, ics):
+    """Opt-in corrected walk: matches the oracle's fixed walk bit for bit and is far closer to the direct sum."""
+    abi, _ = gb.load()
+    x, v, m, G = ics.plummer(20000, 33)
+    exact = gb.acceleration(x, m, G, "pairwise", 0.01)
+    ref_mode = gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)
+    gb.check_rc(abi.grav_b200_set_bh_mode(gb.BH_FIXED))
+    try:
+        fixed = gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)
+    finally:
+        gb.check_rc(abi.grav_b200_set_bh_mode(gb.BH_REFERENCE))
+    assert np.array_equal(fixed, oracle.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1, fixed=True))
+    err = lambda a: float(np.mean(np.linalg.norm(a - exact, axis=1) / np.linalg.norm(exact, axis=1)))
+    assert err(fixed) < 0.02 < err(ref_mode)
+
+
+def test_bh_full_size_properties(gb, ics):
+    """N = 2^20 (the BH bench size): determinism and tree invariants that do not need the CPU oracle."""
+    n = 1 << 20
+    x, v, m, G = ics.plummer(n, 77)
+    t = gb.construct_octree(x, m, 1)
+    assert np.all(np.diff(t["keys"]) >= 0)                                   # sortedness
+    assert np.array_equal(np.sort(t["sorted_indices"]), np.arange(n))        # a permutation
+    same = t["keys"][1:] == t["keys"][:-1]
+    assert np.all(t["sorted_indices"][1:][same] > t["sorted_indices"][:-1][same])   # stable
+    nch, fc, npart = t["num_children"], t["first_child"], t["num_particles"]
+    internal = np.nonzero(nch > 0)[0]
+    assert t["num_nodes"] == 1 + nch.sum()
+    assert npart[0] == n and abs(t["mass"][0] - m.sum()) < 1e-12
+    # children partition their parent
+    csum = np.add.reduceat(npart[1:], (fc[internal] - 1)[np.argsort(fc[internal])])
+    assert np.array_equal(np.sort(csum), np.sort(npart[internal]))
+    a1 = gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)
+    a2 = gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)
+    assert np.array_equal(a1, a2) and np.isfinite(a1).all()

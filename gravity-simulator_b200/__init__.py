@@ -99,7 +99,7 @@ ABI_SYMBOLS = [
     "grav_b200_ctx_create", "grav_b200_ctx_destroy", "grav_b200_nccl_unique_id", "grav_b200_ctx_set_system",
     "grav_b200_ctx_set_positions", "grav_b200_ctx_num_particles", "grav_b200_ctx_owned_range",
     "grav_b200_ctx_acceleration", "grav_b200_ctx_get_positions", "grav_b200_ctx_get_velocities",
-    "grav_b200_ctx_get_accelerations", "grav_b200_ctx_leapfrog_begin", "grav_b200_ctx_leapfrog_steps",
+    "grav_b200_ctx_get_accelerations", "grav_b200_ctx_leapfrog_begin", "grav_b200_ctx_leapfrog_steps", "grav_b200_ctx_leapfrog_end",
     "grav_b200_ctx_energy", "grav_b200_ctx_synchronize", "grav_b200_ctx_last_timing_ms",
     "grav_b200_kernel_launch_count", "grav_b200_measure_fp64_peak", "grav_b200_ctx_event_record",
     "grav_b200_ctx_event_elapsed_ms", "grav_b200_ctx_flush_l2", "grav_b200_ctx_mark_positions_sharded",
@@ -142,7 +142,8 @@ def load():
     abi.grav_b200_ctx_acceleration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]
     for f in ("positions", "velocities", "accelerations"):
         getattr(abi, f"grav_b200_ctx_get_{f}").argtypes = [C.c_void_p, c_double_p]
-    abi.grav_b200_ctx_leapfrog_begin.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]
+    abi.grav_b200_ctx_leapfrog_begin.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double]
+    abi.grav_b200_ctx_leapfrog_end.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_leapfrog_steps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
     abi.grav_b200_ctx_energy.argtypes = [C.c_void_p, c_double_p]
     abi.grav_b200_ctx_synchronize.argtypes = [C.c_void_p]
@@ -374,10 +375,13 @@ class Context:
     def accelerations(self, out=None):
         return self._get("accelerations", out)
 
-    def leapfrog_begin(self, method="pairwise", softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=-1):
+    def leapfrog_begin(self, dt, method="pairwise", softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=-1):
         meth = METHODS[method] if isinstance(method, str) else int(method)
         check_rc(self.abi.grav_b200_ctx_leapfrog_begin(self.h, meth, float(softening_length), float(opening_angle),
-                                                       int(max_num_particles_per_leaf)))
+                                                       int(max_num_particles_per_leaf), float(dt)))
+
+    def leapfrog_end(self):
+        check_rc(self.abi.grav_b200_ctx_leapfrog_end(self.h))
 
     def leapfrog_steps(self, dt, num_steps):
         check_rc(self.abi.grav_b200_ctx_leapfrog_steps(self.h, float(dt), int(num_steps)))

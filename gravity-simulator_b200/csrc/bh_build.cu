@@ -38,14 +38,6 @@ struct ExpRec {       // one expanded (= has children) node, 64 bytes
 };
 static_assert(sizeof(ExpRec) == 64, "ExpRec layout");
 
-struct WalkNode {     // what the tree walk reads per node, 64 bytes
-    double mass, cx, cy, cz;
-    long long kq;     // key the inclusion test compares against (mode dependent)
-    int first, count, nch, fc;
-    long long pad;
-};
-static_assert(sizeof(WalkNode) == 64, "WalkNode layout");
-
 int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);
 int bh_keys(grav_b200_ctx *c, const double *box_center, double box_width, bool want_unsorted);
 int radix_sort_pairs(grav_b200_ctx *c);
@@ -209,12 +201,30 @@ __global__ void __launch_bounds__(256) walk_nodes_kernel(int M, const int *__res
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= M) return;
-    WalkNode w;
-    w.mass = mass[id]; w.cx = cx[id]; w.cy = cy[id]; w.cz = cz[id];
-    w.first = first[id]; w.count = np[id]; w.nch = nchild[id]; w.fc = fc[id];
-    w.kq = fixed_mode ? K[w.first] : K[perm[w.first]];
-    w.pad = 0;
-    out[id] = w;
+    WalkNode *w = out + id;      // next / level are written by rope_kernel
+    const int f = first[id];
+    w->cx = cx[id]; w->cy = cy[id]; w->cz = cz[id];
+    w->kq = fixed_mode ? K[f] : K[perm[f]];
+    w->fc = nchild[id] > 0 ? fc[id] : -1;
+    w->count = np[id];
+    w->mass = mass[id];
+    w->first = f;
+    w->pad = 0;
+    if (id == 0) { w->next = -1; w->level = 0; }
+}
+
+// Ropes, one level at a time from the root down: the last child inherits its parent's rope.
+__global__ void __launch_bounds__(256) rope_kernel(const ExpRec *__restrict__ rec, int begin, int count, WalkNode *__restrict__ nodes)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const ExpRec r = rec[begin + t];
+    const int my_next = (r.id == 0) ? -1 : nodes[r.id].next;
+    for (int k = 0; k < r.nch; k++) {
+        const int cid = r.first_child + k;
+        nodes[cid].next = (k < r.nch - 1) ? cid + 1 : my_next;
+        nodes[cid].level = r.level + 1;
+    }
 }
 
 static int grow_preserve(grav_b200_ctx *c, DevBuf &buf, size_t used_bytes, size_t need_bytes)
@@ -293,6 +303,7 @@ int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double bo
     const int ne = level_off[levels];
     t.num_expanded = ne;
     t.max_level = levels;
+    for (int l = 0; l <= levels; l++) t.level_off[l] = level_off[l];
 
     // numbering
     GB_TRY(exclusive_scan_int(c, t.wsum.as<int>(), t.wscan.as<int>(), n + 1, t.scan_tmp));
@@ -348,13 +359,20 @@ int bh_pack_walk_nodes(grav_b200_ctx *c)
     DevTree &t = c->tree;
     const int M = t.num_nodes;
     GB_TRY(t.node_walk.reserve(sizeof(WalkNode) * (size_t)M));
+    WalkNode *nodes = t.node_walk.as<WalkNode>();
     walk_nodes_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(M, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
                                                             t.node_fc.as<int>(), t.node_mass.as<double>(), t.node_cx.as<double>(),
                                                             t.node_cy.as<double>(), t.node_cz.as<double>(), t.keys.as<long long>(),
-                                                            t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0,
-                                                            t.node_walk.as<WalkNode>());
+                                                            t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0, nodes);
     GB_LAUNCH_CHECK();
     count_launch();
+    for (int l = 0; l < t.max_level; l++) {
+        const int begin = t.level_off[l], count = t.level_off[l + 1] - begin;
+        if (count <= 0) continue;
+        rope_kernel<<<(count + 255) / 256, 256, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, nodes);
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
     return GRAV_B200_OK;
 }
 

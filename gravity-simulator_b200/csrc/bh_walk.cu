@@ -1,11 +1,18 @@
 // Barnes-Hut stage BH-8 on the device: the tree walk.
 //
-// Reference: helper_compute_acceleration (src/acceleration_barnes_hut.c:78-248): one thread per particle
-// (in Morton order) runs a depth-first walk with a private stack.  Here a WARP walks the tree for 32
-// Morton-adjacent targets at once: control flow, the stack (shared memory, <= 22 frames) and the node
-// records (one 64-byte load, same address for all lanes) are warp-uniform; each frame carries the mask of
-// lanes that still need the subtree.  A lane that accepts a node leaves the mask for that subtree, so every
-// lane sees exactly the nodes, in exactly the depth-first order, that the reference's per-particle walk sees.
+// Reference: helper_compute_acceleration (src/acceleration_barnes_hut.c:78-248): one CPU thread per particle
+// (in Morton order) runs a depth-first walk with a private 22-frame stack.
+//
+// Here: one GPU thread per target, targets taken in Morton order so the 32 lanes of a warp follow nearly the
+// same path (their node loads then hit the same sectors), and the walk is STACKLESS: every node record carries
+// a rope (`next`, the node that follows in depth-first order when the subtree is skipped), so a visit is
+//     accept or leaf  ->  node = next          open  ->  node = first child
+// and each lane advances through exactly the nodes, in exactly the order, the reference visits for that
+// particle.  A first version shared one traversal per warp (union of the lanes' trees, per-lane masks); the ncu
+// profile (profiles/r1_walk_warp_union.txt) showed it issue-bound with 7 of 32 lanes active in the accept path
+// and 4.4x more node visits than a single particle needs, because the opening test separates Morton
+// neighbours.  Independent lanes remove both costs.
+//
 // All arithmetic that feeds a decision or the result uses IEEE operations without FMA contraction
 // (__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn) in the reference's order, so in reference mode the output is
 // bit-identical to the x86-64 reference build.
@@ -20,14 +27,8 @@
 namespace gb {
 
 constexpr int MAX_LEVEL = 21;
-constexpr int WALK_WARPS = 8;
-
-struct WalkNode {     // must match bh_build.cu
-    double mass, cx, cy, cz;
-    long long kq;
-    int first, count, nch, fc;
-    long long pad;
-};
+constexpr int WALK_BLOCK = 128;
+constexpr int WALK_POOL = WALK_BLOCK;       // targets per CTA; > WALK_BLOCK enables per-lane work fetching (measured slower: 46 vs 41 ms, N=2^20 Plummer)
 
 struct WalkArgs {
     const WalkNode *nodes;
@@ -40,119 +41,115 @@ struct WalkArgs {
     double *acc;             // AoS [3n] by particle id
 };
 
-__device__ __forceinline__ WalkNode load_node(const WalkNode *p)
+struct NodeRec {   // the 48 bytes of a WalkNode every visit needs, as loaded (three 16-byte read-only loads)
+    int4 A, B, C;
+};
+__device__ __forceinline__ NodeRec load_rec(const WalkNode *nodes, int node)
 {
-    // four 16-byte read-only loads; every lane of the warp reads the same address (one transaction each)
-    const int4 *q = reinterpret_cast<const int4 *>(p);
-    int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    WalkNode w;
-    w.mass = __hiloint2double(a.y, a.x);
-    w.cx = __hiloint2double(a.w, a.z);
-    w.cy = __hiloint2double(b.y, b.x);
-    w.cz = __hiloint2double(b.w, b.z);
-    w.kq = ((long long)c.y << 32) | (unsigned)c.x;
-    w.first = c.z;
-    w.count = c.w;
-    const int2 d = __ldg(reinterpret_cast<const int2 *>(p) + 6);
-    w.nch = d.x;
-    w.fc = d.y;
-    w.pad = 0;
-    return w;
+    const int4 *q = reinterpret_cast<const int4 *>(nodes + node);
+    NodeRec r;
+    r.A = __ldg(q); r.B = __ldg(q + 1); r.C = __ldg(q + 2);
+    return r;
 }
 
+// Per-lane state machine.  Each trip of the loop handles ONE item for the lane -- a node visit, or the next
+// particle of a leaf that is being summed directly -- in three steps that are the same code for every lane:
+//   decide    opening test on the current node record -> the next node id, and possibly a source (R, d2, m)
+//   prefetch  the record of the next node is requested BEFORE the arithmetic below, so its L1/L2 latency
+//             overlaps the sqrt/div sequence
+//   evaluate  f = G m / r^3 and the three accumulator updates, shared by accepted nodes and leaf particles
+//             (both are sqrt(((rx^2+ry^2)+rz^2)+eps^2) in the reference, :164-171 and :198-213)
 template <bool FIXED>
-__global__ void __launch_bounds__(WALK_WARPS * 32) walk_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(WALK_BLOCK) walk_kernel(const WalkArgs a)
 {
-    // saved frames of the enclosing levels; the current frame lives in (warp-uniform) registers
-    __shared__ int s_fc[WALK_WARPS][MAX_LEVEL + 1], s_n[WALK_WARPS][MAX_LEVEL + 1], s_j[WALK_WARPS][MAX_LEVEL + 1];
-    __shared__ unsigned s_mask[WALK_WARPS][MAX_LEVEL + 1];
     __shared__ double s_cell2[MAX_LEVEL + 2];
+    __shared__ int s_next;   // next unclaimed target of this CTA's pool
     if (threadIdx.x < MAX_LEVEL + 2) s_cell2[threadIdx.x] = a.cell2[threadIdx.x];
+    // Work distribution: a CTA owns a pool of WALK_POOL Morton-consecutive targets.  A lane that finishes its
+    // particle claims the next one of the pool (shared-memory counter), so lanes with short walks do not idle
+    // behind lanes with long ones.  In reference mode walk lengths differ wildly even between Morton
+    // neighbours, because the inclusion test uses an unrelated particle's key (see file header).
+    const int pool_lo = a.p_lo + blockIdx.x * WALK_POOL;
+    const int pool_hi = min(pool_lo + WALK_POOL, a.p_hi);
+    if (threadIdx.x == 0) s_next = pool_lo + WALK_BLOCK;
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = a.p_lo + (blockIdx.x * WALK_WARPS + warp) * 32 + lane;
-    const bool valid = p < a.p_hi;
-    int idx = -1;
-    double xi = 0.0, yi = 0.0, zi = 0.0;
-    long long ki = 0;
-    if (valid) {
-        idx = a.perm[p];
-        const double4 q = a.posm[idx];
-        xi = q.x; yi = q.y; zi = q.z;
-        ki = FIXED ? a.K[p] : a.K[idx];
-    }
-    double ax = 0.0, ay = 0.0, az = 0.0;
-    const unsigned all = __ballot_sync(0xffffffffu, valid);
-    if (all == 0u) return;
+    int p = pool_lo + threadIdx.x;
+    const int root_fc = __ldg(&a.nodes[0].fc);   // the root is always expanded
 
-    int depth = 0;
-    int cur_fc, cur_n, cur_j = 0;
-    unsigned cur_mask = all;
-    {
-        const WalkNode root = load_node(a.nodes);
-        cur_fc = root.fc;
-        cur_n = root.nch;
-    }
-    while (true) {
-        if (cur_j >= cur_n) {           // frame exhausted: pop
-            if (depth == 0) break;
-            depth--;
-            cur_fc = s_fc[warp][depth]; cur_n = s_n[warp][depth]; cur_j = s_j[warp][depth]; cur_mask = s_mask[warp][depth];
-            continue;
-        }
-        const int c = cur_fc + cur_j;
-        cur_j++;
-        const int level = depth + 1;
-        const int shift = 3 * (MAX_LEVEL - level);
-        const WalkNode nd = load_node(a.nodes + c);
-        const bool leaf = nd.nch <= 0;
-        bool need = false;
-        if ((cur_mask >> lane) & 1u) {
-            const bool inside = (ki >> shift) == (nd.kq >> shift);
-            bool accepted = false;
-            if (FIXED ? (!inside && !leaf) : !inside) {
-                const double rx = __dsub_rn(xi, nd.cx), ry = __dsub_rn(yi, nd.cy), rz = __dsub_rn(zi, nd.cz);
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                if (s_cell2[level] < __dmul_rn(a.theta2, d2)) {
-                    const double r = __dsqrt_rn(__dadd_rn(d2, a.eps2));
-                    const double f = __ddiv_rn(__dmul_rn(a.G, nd.mass), __dmul_rn(__dmul_rn(r, r), r));
-                    ax = __dsub_rn(ax, __dmul_rn(f, rx));
-                    ay = __dsub_rn(ay, __dmul_rn(f, ry));
-                    az = __dsub_rn(az, __dmul_rn(f, rz));
-                    accepted = true;
+    while (p < pool_hi) {
+        const int idx = a.perm[p];
+        const double4 me = a.posm[idx];
+        const double xi = me.x, yi = me.y, zi = me.z;
+        const long long ki = FIXED ? a.K[p] : a.K[idx];
+        double ax = 0.0, ay = 0.0, az = 0.0;
+
+        int node = root_fc;
+        NodeRec rec = load_rec(a.nodes, node);
+        int leaf_pos = 0, leaf_rem = 0, leaf_next = -1;
+        while (node >= 0) {
+            bool have = false;
+            double rx = 0.0, ry = 0.0, rz = 0.0, d2 = 0.0, msrc = 0.0;
+            int new_node = node;
+            if (leaf_rem == 0) {
+                const double cx = __hiloint2double(rec.A.y, rec.A.x), cy = __hiloint2double(rec.A.w, rec.A.z);
+                const double cz = __hiloint2double(rec.B.y, rec.B.x);
+                const long long kq = ((long long)rec.B.w << 32) | (unsigned)rec.B.z;
+                const int fc = rec.C.x, next = rec.C.y, level = rec.C.z, count = rec.C.w;
+                const int shift = 3 * (MAX_LEVEL - level);
+                const bool leaf = fc < 0;
+                const bool inside = ((ki ^ kq) >> shift) == 0;
+                bool accepted = false;
+                if (FIXED ? (!inside && !leaf) : !inside) {
+                    rx = __dsub_rn(xi, cx); ry = __dsub_rn(yi, cy); rz = __dsub_rn(zi, cz);
+                    d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                    accepted = s_cell2[level] < __dmul_rn(a.theta2, d2);
+                }
+                if (accepted) {
+                    msrc = __ldg(&a.nodes[node].mass);
+                    have = true;
+                    new_node = next;
+                } else if (leaf) {
+                    leaf_pos = __ldg(&a.nodes[node].first);
+                    leaf_rem = count;
+                    leaf_next = next;
+                } else {
+                    new_node = fc;
                 }
             }
-            need = !accepted;
-        }
-        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-        if (need_mask == 0u) continue;
-        if (leaf) {
-            // direct sum over the leaf's particles (sorted order), skipping the target itself
-            for (int k = 0; k < nd.count; k++) {
-                const int jdx = __ldg(a.perm + nd.first + k);
-                const double4 q = a.posm[jdx];
-                if (need && jdx != idx) {
-                    const double rx = __dsub_rn(xi, q.x), ry = __dsub_rn(yi, q.y), rz = __dsub_rn(zi, q.z);
-                    const double d2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)), a.eps2);
-                    const double r = __dsqrt_rn(d2);
-                    const double f = __ddiv_rn(__dmul_rn(a.G, q.w), __dmul_rn(__dmul_rn(r, r), r));
-                    ax = __dsub_rn(ax, __dmul_rn(f, rx));
-                    ay = __dsub_rn(ay, __dmul_rn(f, ry));
-                    az = __dsub_rn(az, __dmul_rn(f, rz));
+            if (leaf_rem > 0) {   // one particle of the leaf per trip (sorted order), skipping the target itself
+                const int jdx = __ldg(a.perm + leaf_pos);
+                leaf_pos++;
+                leaf_rem--;
+                if (jdx != idx) {
+                    const double4 pj = a.posm[jdx];
+                    rx = __dsub_rn(xi, pj.x); ry = __dsub_rn(yi, pj.y); rz = __dsub_rn(zi, pj.z);
+                    d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                    msrc = pj.w;
+                    have = true;
                 }
+                if (leaf_rem == 0) new_node = leaf_next;
             }
-        } else {
-            // push: every lane stores the same (uniform) values; only this warp ever touches its rows, and the
-            // reads on pop are separated from these writes by the ballot above / program order within a lane
-            s_fc[warp][depth] = cur_fc; s_n[warp][depth] = cur_n; s_j[warp][depth] = cur_j; s_mask[warp][depth] = cur_mask;
-            depth++;
-            cur_fc = nd.fc; cur_n = nd.nch; cur_j = 0; cur_mask = need_mask;
+            if (new_node != node && new_node >= 0) rec = load_rec(a.nodes, new_node);
+            node = new_node;
+            if (have) {
+                const double s = __dadd_rn(d2, a.eps2);
+                const double gm = __dmul_rn(a.G, msrc);
+                double f;
+                if (gm == 0.0 && s > 1e-200 && s < 1e200) {
+                    f = gm;     // 0 / r^3 with r^3 finite and positive: exactly the signed zero gm (dropped zero-mass leaves)
+                } else {
+                    const double r = __dsqrt_rn(s);
+                    f = __ddiv_rn(gm, __dmul_rn(__dmul_rn(r, r), r));
+                }
+                ax = __dsub_rn(ax, __dmul_rn(f, rx));
+                ay = __dsub_rn(ay, __dmul_rn(f, ry));
+                az = __dsub_rn(az, __dmul_rn(f, rz));
+            }
         }
-    }
-    if (valid) {
         a.acc[3 * (size_t)idx + 0] = ax;
         a.acc[3 * (size_t)idx + 1] = ay;
         a.acc[3 * (size_t)idx + 2] = az;
+        p = atomicAdd(&s_next, 1);
     }
 }
 
@@ -182,9 +179,9 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
     if (c->world > 1) GB_CUDA(cudaMemsetAsync(a.acc, 0, sizeof(double) * 3 * (size_t)c->n, c->stream));
     const int npos = a.p_hi - a.p_lo;
     if (npos > 0) {
-        const int blocks = (npos + WALK_WARPS * 32 - 1) / (WALK_WARPS * 32);
-        if (c->bh_mode == GRAV_B200_BH_FIXED) walk_kernel<true><<<blocks, WALK_WARPS * 32, 0, c->stream>>>(a);
-        else walk_kernel<false><<<blocks, WALK_WARPS * 32, 0, c->stream>>>(a);
+        const int blocks = (npos + WALK_POOL - 1) / WALK_POOL;
+        if (c->bh_mode == GRAV_B200_BH_FIXED) walk_kernel<true><<<blocks, WALK_BLOCK, 0, c->stream>>>(a);
+        else walk_kernel<false><<<blocks, WALK_BLOCK, 0, c->stream>>>(a);
         GB_LAUNCH_CHECK();
         count_launch();
     }

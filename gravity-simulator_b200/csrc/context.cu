@@ -227,10 +227,10 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     comm_destroy(c);
     DevBuf *bufs[] = {&c->posm, &c->vel, &c->acc, &c->xcomp, &c->vcomp, &c->stage_a, &c->stage_b, &c->stage_c, &c->stage_d,
-                      &c->partials, &c->misc, &c->msrc, &c->msrc_id, &c->msrc_altm, &c->l2_flush};
+                      &c->partials, &c->misc, &c->msrc, &c->msrc_id, &c->msrc_altm, &c->l2_flush, &c->mflag, &c->mrank};
     for (DevBuf *b : bufs) b->release();
     DevTree &t = c->tree;
-    DevBuf *tb[] = {&t.keys_unsorted, &t.keys, &t.perm, &t.keys_tmp, &t.perm_tmp, &t.hist, &t.bbox, &t.exp_rec, &t.level_off,
+    DevBuf *tb[] = {&t.keys_unsorted, &t.keys, &t.perm, &t.keys_tmp, &t.perm_tmp, &t.hist, &t.bbox, &t.exp_rec,
                     &t.wsum, &t.wscan, &t.scan_tmp, &t.fc, &t.node_np, &t.node_nch, &t.node_first, &t.node_fc, &t.node_mass,
                     &t.node_cx, &t.node_cy, &t.node_cz, &t.node_mtd, &t.node_walk, &t.ki, &t.counters};
     for (DevBuf *b : tb) b->release();
@@ -349,7 +349,10 @@ int grav_b200_ctx_get_positions(grav_b200_ctx *c, double *x)
 int grav_b200_ctx_get_velocities(grav_b200_ctx *c, double *v)
 {
     if (!c || !v || c->n < 1) { set_error("context has no system / NULL pointer"); return GRAV_B200_EINVAL; }
-    return download_aos3(c, c->vel.as<double>(), v, true);
+    GB_CUDA(cudaSetDevice(c->device));
+    double *d_v;
+    GB_TRY(synced_velocities(c, &d_v));
+    return download_aos3(c, d_v, v, true);
 }
 int grav_b200_ctx_get_accelerations(grav_b200_ctx *c, double *a)
 {
@@ -463,9 +466,9 @@ static int whfast_one_shot(double *a, int n, const double *x, const double *m, d
     GB_TRY(c->stage_d.reserve(sizeof(double) * (size_t)n));
     GB_CUDA(cudaMemcpyAsync(c->stage_c.p, jx, b3, cudaMemcpyHostToDevice, c->stream));
     GB_CUDA(cudaMemcpyAsync(c->stage_d.p, eta, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    // the reference never writes a[0..2] (loops start at particle 1, src/integrator_whfast.c:858,1021,1131):
-    // keep the caller's values there
-    GB_CUDA(cudaMemcpyAsync(c->acc.p, a, sizeof(double) * 3, cudaMemcpyHostToDevice, c->stream));
+    // the reference leaves some entries of a[] untouched (particle 0 and, in the massless variant, the first
+    // massive particle: loops start at 1, src/integrator_whfast.c:858,1012,1131): start from the caller's values
+    GB_CUDA(cudaMemcpyAsync(c->acc.p, a, b3, cudaMemcpyHostToDevice, c->stream));
     GB_TRY(whfast_accel(c, c->stage_c.as<double>(), c->stage_d.as<double>(), eps, massless));
     return grav_b200_ctx_get_accelerations(c, a);
 }

@@ -372,13 +372,16 @@ __global__ void massless_compact_kernel(const double4 *__restrict__ posm, int n,
 
 int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);   // scan.cu
 
-int direct_sum_massless(grav_b200_ctx *c, double eps)
+// Massive-particle list of the resident system: c->msrc (packed records), c->msrc_id (particle ids, index order),
+// c->msrc_altm (m[rank] quirk masses), c->mrank (list position of every massive particle).  Shared by the massless
+// direct sum and the WHFast massless kernel.
+int massive_list(grav_b200_ctx *c, int *n_massive_out)
 {
     const int n = c->n;
-    GB_TRY(c->stage_c.reserve(sizeof(int) * (size_t)(n + 1)));
-    GB_TRY(c->stage_d.reserve(sizeof(int) * (size_t)(n + 1)));
-    int *flag = c->stage_c.as<int>();
-    int *rank = c->stage_d.as<int>();
+    GB_TRY(c->mflag.reserve(sizeof(int) * (size_t)(n + 1)));
+    GB_TRY(c->mrank.reserve(sizeof(int) * (size_t)(n + 1)));
+    int *flag = c->mflag.as<int>();
+    int *rank = c->mrank.as<int>();
     const int nb = (n + 255) / 256;
     GB_CUDA(cudaMemsetAsync(flag + n, 0, sizeof(int), c->stream));
     massless_flags_kernel<<<nb, 256, 0, c->stream>>>(c->posm.as<double4>(), n, flag);
@@ -401,6 +404,14 @@ int direct_sum_massless(grav_b200_ctx *c, double eps)
         GB_LAUNCH_CHECK();
         count_launch();
     }
+    *n_massive_out = n_massive;
+    return GRAV_B200_OK;
+}
+
+int direct_sum_massless(grav_b200_ctx *c, double eps)
+{
+    int n_massive = 0;
+    GB_TRY(massive_list(c, &n_massive));
     DSArgs a{};
     a.src = c->msrc.as<double4>();
     a.src_id = c->msrc_id.as<int>();

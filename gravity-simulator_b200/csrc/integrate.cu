@@ -1,0 +1,225 @@
+// Device-resident leapfrog (kick-drift-kick with compensated summation) and the energy diagnostic.
+//
+// Reference: leapfrog(), src/integrator.c:894-1121 -- initial a(x0) and half kick (:963-982), per step a drift
+// (:1009-1018), a force evaluation (:1021) and a full kick (:1030-1039), with Kahan-style error terms for x and v;
+// velocities are brought back to the position time level with v -= a dt / 2 only for snapshots and at the end
+// (:1048-1056, :1088-1094).  Energy: compute_energy(), src/utils.c:27-59 (unsoftened potential).
+//
+// The update kernels use the reference's exact operation order without FMA contraction, so with bit-identical
+// accelerations (Barnes-Hut in reference mode) the trajectory is bit-identical to the reference's; with the
+// direct sum it differs only through the 1e-15-level differences of the accelerations.
+// Every rank updates its owned particle range only; the position shards are gathered by the next force call.
+#include "internal.cuh"
+
+namespace gb {
+
+// c += a*scale*dt ; v = v0 + c ; c += v0 - v      (reference: v_err += [0.5 *] a * dt; v = tmp + v_err; v_err += tmp - v)
+__global__ void __launch_bounds__(256) kick_kernel(double *__restrict__ v, double *__restrict__ vc, const double *__restrict__ a,
+                                                  size_t lo, size_t hi, double dt, int half)
+{
+    const size_t k = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= hi) return;
+    const double inc = half ? __dmul_rn(__dmul_rn(0.5, a[k]), dt) : __dmul_rn(a[k], dt);
+    double c = __dadd_rn(vc[k], inc);
+    const double v0 = v[k];
+    const double v1 = __dadd_rn(v0, c);
+    c = __dadd_rn(c, __dsub_rn(v0, v1));
+    v[k] = v1;
+    vc[k] = c;
+}
+
+__global__ void __launch_bounds__(256) drift_kernel(double4 *__restrict__ posm, double *__restrict__ xc, const double *__restrict__ v,
+                                                   int lo, int hi, double dt)
+{
+    const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    double4 q = posm[i];
+    double *pc = xc + 3 * (size_t)i;
+    const double *pv = v + 3 * (size_t)i;
+    double x0[3] = {q.x, q.y, q.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double c = __dadd_rn(pc[k], __dmul_rn(pv[k], dt));
+        const double x1 = __dadd_rn(x0[k], c);
+        c = __dadd_rn(c, __dsub_rn(x0[k], x1));
+        pc[k] = c;
+        x0[k] = x1;
+    }
+    q.x = x0[0]; q.y = x0[1]; q.z = x0[2];
+    posm[i] = q;
+}
+
+// out = v - 0.5*a*dt  (velocities at the position time level)
+__global__ void __launch_bounds__(256) vsync_kernel(const double *__restrict__ v, const double *__restrict__ a, double *__restrict__ out,
+                                                   size_t lo, size_t hi, double dt)
+{
+    const size_t k = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= hi) return;
+    out[k] = __dsub_rn(v[k], __dmul_rn(__dmul_rn(0.5, a[k]), dt));
+}
+
+static int run_force(grav_b200_ctx *c)
+{
+    return grav_b200_ctx_acceleration(c, c->lf_method, c->lf_eps, c->lf_theta, c->lf_leaf);
+}
+
+static int kick(grav_b200_ctx *c, double dt, int half)
+{
+    const size_t lo = 3 * (size_t)c->lo, hi = 3 * (size_t)c->hi;
+    if (hi <= lo) return GRAV_B200_OK;
+    kick_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(c->vel.as<double>(), c->vcomp.as<double>(), c->acc.as<double>(),
+                                                                           lo, hi, dt, half);
+    GB_LAUNCH_CHECK();
+    count_launch();
+    return GRAV_B200_OK;
+}
+
+// velocities synchronised with the positions: the stored ones while no leapfrog is running, else v - a dt/2
+int synced_velocities(grav_b200_ctx *c, double **d_out)
+{
+    if (!c->lf_ready) { *d_out = c->vel.as<double>(); return GRAV_B200_OK; }
+    GB_TRY(c->stage_b.reserve(sizeof(double) * 3 * (size_t)c->n));
+    const size_t lo = 3 * (size_t)c->lo, hi = 3 * (size_t)c->hi;
+    if (hi > lo) {
+        vsync_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(c->vel.as<double>(), c->acc.as<double>(),
+                                                                                c->stage_b.as<double>(), lo, hi, c->lf_dt);
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
+    *d_out = c->stage_b.as<double>();
+    return GRAV_B200_OK;
+}
+
+// ---- energy -------------------------------------------------------------------------------------------
+// E = sum_i m_i |v_i|^2 / 2  -  G sum_{i<j} m_i m_j / |x_i - x_j|.  Each thread owns one particle i and sums
+// m_j / r_ij over all j != i (tiles through shared memory), so the pair sum is G/2 sum_i m_i pot_i.  Block
+// partial sums are written out and added in block order by one thread: deterministic.
+__global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__ posm, const double *__restrict__ v, int n, int n_pad,
+                                                    int lo, int hi, double G, double *__restrict__ block_out)
+{
+    __shared__ double4 tile[256];
+    __shared__ double red[256];
+    const int i = lo + blockIdx.x * 256 + threadIdx.x;
+    const bool valid = i < hi;
+    double4 me = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (valid) me = posm[i];
+    double pot = 0.0;
+    for (int j0 = 0; j0 < n_pad; j0 += 256) {
+        __syncthreads();
+        tile[threadIdx.x] = posm[j0 + threadIdx.x];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < 256; j++) {
+            const double4 q = tile[j];
+            const double dx = q.x - me.x, dy = q.y - me.y, dz = q.z - me.z;
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            // padding has m = 0; the self term (and exact coincidences) have r2 = 0: skip both
+            if (r2 > 0.0 && (j0 + j) < n) pot += q.w / sqrt(r2);
+        }
+    }
+    double e = 0.0;
+    if (valid) {
+        const double vx = v[3 * (size_t)i], vy = v[3 * (size_t)i + 1], vz = v[3 * (size_t)i + 2];
+        e = 0.5 * me.w * (vx * vx + vy * vy + vz * vz) - 0.5 * G * me.w * pot;
+    }
+    red[threadIdx.x] = e;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_out[blockIdx.x] = red[0];
+}
+
+__global__ void sum_blocks_kernel(const double *__restrict__ in, int count, double *__restrict__ out)
+{
+    double s = 0.0;
+    for (int k = 0; k < count; k++) s += in[k];
+    out[0] = s;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *c, int method, double eps, double theta, int max_leaf, double dt)
+{
+    if (!c || c->n < 1) { set_error("context has no system"); return GRAV_B200_EINVAL; }
+    GB_CUDA(cudaSetDevice(c->device));
+    const size_t b3 = sizeof(double) * 3 * (size_t)c->n;
+    GB_TRY(c->xcomp.reserve(b3));
+    GB_TRY(c->vcomp.reserve(b3));
+    GB_CUDA(cudaMemsetAsync(c->xcomp.p, 0, b3, c->stream));
+    GB_CUDA(cudaMemsetAsync(c->vcomp.p, 0, b3, c->stream));
+    c->lf_method = method; c->lf_eps = eps; c->lf_theta = theta; c->lf_leaf = max_leaf;
+    c->lf_ready = false;
+    GB_TRY(run_force(c));               // a(x0), src/integrator.c:963
+    GB_TRY(kick(c, dt, 1));             // v_{1/2}, :973-982
+    c->lf_dt = dt;
+    c->lf_ready = true;
+    return GRAV_B200_OK;
+}
+
+int grav_b200_ctx_leapfrog_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
+{
+    if (!c || !c->lf_ready) { set_error("leapfrog_begin() has not been called"); return GRAV_B200_EINVAL; }
+    GB_CUDA(cudaSetDevice(c->device));
+    for (int64_t s = 0; s < num_steps; s++) {
+        const int cnt = c->hi - c->lo;
+        if (cnt > 0) {
+            drift_kernel<<<(cnt + 255) / 256, 256, 0, c->stream>>>(c->posm.as<double4>(), c->xcomp.as<double>(), c->vel.as<double>(),
+                                                                  c->lo, c->hi, dt);   // :1009-1018
+            GB_LAUNCH_CHECK();
+            count_launch();
+        }
+        if (c->world > 1) c->posm_gathered = false;
+        GB_TRY(run_force(c));           // :1021
+        GB_TRY(kick(c, dt, 0));         // :1030-1039
+        c->lf_dt = dt;
+    }
+    return GRAV_B200_OK;
+}
+
+int grav_b200_ctx_leapfrog_end(grav_b200_ctx *c)
+{
+    if (!c || !c->lf_ready) { set_error("leapfrog_begin() has not been called"); return GRAV_B200_EINVAL; }
+    GB_CUDA(cudaSetDevice(c->device));
+    const size_t lo = 3 * (size_t)c->lo, hi = 3 * (size_t)c->hi;
+    if (hi > lo) {   // v -= a dt / 2 in place, :1088-1094
+        vsync_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(c->vel.as<double>(), c->acc.as<double>(), c->vel.as<double>(),
+                                                                                lo, hi, c->lf_dt);
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
+    c->lf_ready = false;
+    return GRAV_B200_OK;
+}
+
+int grav_b200_ctx_energy(grav_b200_ctx *c, double *energy)
+{
+    if (!c || !energy || c->n < 1) { set_error("context has no system / NULL pointer"); return GRAV_B200_EINVAL; }
+    GB_CUDA(cudaSetDevice(c->device));
+    if (c->world > 1 && !c->posm_gathered) { GB_TRY(comm_allgather_posm(c)); c->posm_gathered = true; }
+    double *d_v;
+    GB_TRY(synced_velocities(c, &d_v));
+    const int cnt = c->hi - c->lo;
+    const int blocks = (cnt + 255) / 256;
+    GB_TRY(c->misc.reserve(sizeof(double) * ((size_t)blocks + 2)));
+    double *part = c->misc.as<double>();
+    if (blocks > 0) {
+        energy_kernel<<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->G, part + 1);
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
+    sum_blocks_kernel<<<1, 1, 0, c->stream>>>(part + 1, blocks, part);
+    GB_LAUNCH_CHECK();
+    count_launch();
+    GB_TRY(comm_allreduce_sum(c, part, 1));
+    GB_CUDA(cudaMemcpyAsync(energy, part, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    return GRAV_B200_OK;
+}
+
+}  // extern "C"

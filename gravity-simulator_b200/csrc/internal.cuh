@@ -47,18 +47,35 @@ struct DevBuf {
 // Timing stages (grav_b200_ctx_last_timing_ms)
 enum { ST_TOTAL = 0, ST_GATHER = 1, ST_FORCE = 2, ST_MORTON = 3, ST_SORT = 4, ST_BUILD = 5, ST_COUNT = 6 };
 
+// What the tree walk reads per node: one 64-byte record.  The first 48 bytes are needed at every visit,
+// the last 16 only when the node is accepted (mass) or is a leaf that must be summed directly (first).
+// `next` is the "rope": the node that follows in depth-first order when this node's subtree is skipped
+// (next sibling, else the parent's rope; -1 ends the walk), which makes the walk stackless.
+struct WalkNode {
+    double cx, cy, cz;
+    long long kq;      // key the inclusion test compares against (mode dependent)
+    int fc;            // id of the first child, -1 for a leaf
+    int next;
+    int level;
+    int count;         // particles in the node
+    double mass;
+    int first;         // sorted position of the node's first particle
+    int pad;
+};
+static_assert(sizeof(WalkNode) == 64, "WalkNode layout");
+
 // Device-side linear octree (layout in DESIGN.md "BH data layout")
 struct DevTree {
     int n = 0;
     int num_nodes = 0;           // valid after build (host copy)
     int num_expanded = 0;
-    int max_level = 0;
+    int max_level = 0;           // number of levels that hold expanded nodes
+    int level_off[24] = {};      // expanded-node records of level l are [level_off[l], level_off[l+1])
     double box_width = 0.0;
     DevBuf keys_unsorted, keys, perm;       // int64[n], int64[n], int[n]
     DevBuf keys_tmp, perm_tmp, hist;        // radix sort ping-pong + histograms
     DevBuf bbox;                            // double[8]: min xyz, max xyz (ordered-int encoded), then center xyz + width as double[4]
     DevBuf exp_rec;                         // expanded-node records in BFS order
-    DevBuf level_off;                       // int[24] BFS offsets per level (device)
     DevBuf wsum, wscan;                     // int[n+1] children-per-start-position and its exclusive scan
     DevBuf scan_tmp;
     DevBuf fc;                              // int[num_expanded] first-child id per expanded record
@@ -91,12 +108,12 @@ struct grav_b200_ctx {
     gb::DevBuf partials;  // direct-sum split-segment partial sums
     gb::DevBuf misc;      // small scratch (reductions)
     // massless method scratch
-    gb::DevBuf msrc, msrc_id, msrc_altm;
+    gb::DevBuf msrc, msrc_id, msrc_altm, mflag, mrank;
     gb::DevTree tree;
 
     // leapfrog bookkeeping
     int lf_method = 0, lf_leaf = 1;
-    double lf_eps = 0.0, lf_theta = 1.0;
+    double lf_eps = 0.0, lf_theta = 1.0, lf_dt = 0.0;
     bool lf_ready = false;
 
     int bh_mode = 0;
@@ -128,7 +145,7 @@ int comm_allreduce_sum(grav_b200_ctx *c, double *d_val, int count);
 // integrate.cu
 int leapfrog_kick(grav_b200_ctx *c, double dt_half_or_full);
 int leapfrog_drift(grav_b200_ctx *c, double dt);
-int energy(grav_b200_ctx *c, double *out);
+int synced_velocities(grav_b200_ctx *c, double **d_out);
 // timing helpers
 inline void stage_begin(grav_b200_ctx *c, int st) { cudaEventRecord(c->ev[2 * st], c->stream); }
 inline void stage_end(grav_b200_ctx *c, int st) { cudaEventRecord(c->ev[2 * st + 1], c->stream); c->ev_valid[st] = true; }

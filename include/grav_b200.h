@@ -138,14 +138,16 @@ int grav_b200_ctx_get_positions(grav_b200_ctx *ctx, double *x);
 int grav_b200_ctx_get_velocities(grav_b200_ctx *ctx, double *v);
 int grav_b200_ctx_get_accelerations(grav_b200_ctx *ctx, double *a);
 
-/* Leapfrog (kick-drift-kick with compensated summation) on the resident state; mirrors the
- * loop of src/integrator.c:894-1121 (initial a + half kick :963-982, drift :1009-1018,
- * force :1021, kick :1030-1039).  leapfrog_begin() evaluates a(x0) and does nothing else;
- * leapfrog_steps() advances num_steps steps of size dt and leaves x, v synchronised at the
- * same time level (the reference's snapshot convention, :1045-1073). */
+/* Leapfrog (kick-drift-kick with compensated summation) on the resident state; mirrors the loop of
+ * src/integrator.c:894-1121.  leapfrog_begin() zeroes the error terms, evaluates a(x0) and does the initial half
+ * kick with step dt (:963-982), leaving v at the half step.  leapfrog_steps() advances num_steps steps of size dt:
+ * drift (:1009-1018), force (:1021), full kick (:1030-1039).  While a leapfrog is running, get_velocities() and
+ * energy() return velocities brought back to the position time level (v - a dt/2, the reference's snapshot
+ * convention, :1048-1056) without disturbing the state; leapfrog_end() applies that shift in place (:1088-1094). */
 int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *ctx, int method, double softening_length,
-                                 double opening_angle, int max_num_particles_per_leaf);
+                                 double opening_angle, int max_num_particles_per_leaf, double dt);
 int grav_b200_ctx_leapfrog_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
+int grav_b200_ctx_leapfrog_end(grav_b200_ctx *ctx);
 
 /* Total energy of the resident state, same definition as compute_energy, src/utils.c:27-59
  * (unsoftened potential).  Collective when world_size>1. */

@@ -250,3 +250,56 @@ def jacobi_inputs(x, m):
         xcm = xcm * (1.0 + m[i] / eta[i - 1]) + m[i] * jx[i]
     jx[0] = xcm / eta[n - 1]
     return jx, eta
+
+
+# ---- the reference's Python-facing entry point, usable with the reference build AND the drop-in build ------------
+
+DROPIN_SO = HERE / "_ref" / "libgrav_sim_dropin.so"
+INTEGRATORS = {"euler": 1, "euler_cromer": 2, "rk4": 3, "leapfrog": 4, "rkf45": 5, "dopri": 6, "dverk": 7, "rkf78": 8,
+               "ias15": 9, "whfast": 10}   # src/integrator.h:17-26
+
+
+def launch_simulation(lib_path, x, v, m, G, tf, integrator="leapfrog", dt=1e-3, tolerance=1e-9, method="pairwise",
+                      softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=1):
+    """Run launch_simulation_python (src/python_interface.c:94-193) of the given libgrav_sim build with output
+    disabled, exactly as grav_sim/simulator.py:66-102 calls it; returns the final (x, v)."""
+    L = C.CDLL(str(lib_path))
+    x = _f64(x, (-1, 3)).copy(); v = _f64(v, (-1, 3)).copy(); m = _f64(m, (-1,)).copy()
+    n = C.c_int32(m.shape[0])
+    ids = np.arange(m.shape[0], dtype=np.int32)
+    new_ids = C.POINTER(C.c_int32)(); new_x = dp(); new_v = dp(); new_m = dp()
+    is_exit = C.c_bool(False)
+    L.launch_simulation_python.restype = C.c_int
+    rc = L.launch_simulation_python(
+        C.byref(n), ids.ctypes.data_as(C.POINTER(C.c_int32)), _d(x), _d(v), _d(m),
+        C.byref(new_ids), C.byref(new_x), C.byref(new_v), C.byref(new_m),
+        C.c_double(G), C.c_int32(INTEGRATORS[integrator]), C.c_double(dt), C.c_double(tolerance), C.c_double(-1.0),
+        C.c_bool(False), C.c_int32(METHODS[method]), C.c_double(opening_angle), C.c_double(softening_length),
+        C.c_int32(max_num_particles_per_leaf), C.c_int32(1), b"", C.c_bool(False), C.c_double(tf), C.c_int32(2),
+        C.c_int32(2), C.c_int32(2), C.c_int32(0), C.c_bool(False), C.byref(is_exit), C.c_double(tf))
+    if rc != 0:
+        raise RuntimeError(f"launch_simulation_python -> {rc}")
+    return x, v
+
+
+def leapfrog_reference_loop(accel, x, v, m, G, dt, nsteps, energy=None, every=0):
+    """The reference leapfrog (src/integrator.c:963-1094) restated with numpy around a force callback: same update
+    formulas and operation order (numpy multiplies and adds separately, no FMA).  Returns x, synchronised v, and the
+    energies sampled every `every` steps (with the snapshot velocity convention, :1048-1056)."""
+    x = _f64(x, (-1, 3)).copy(); v = _f64(v, (-1, 3)).copy()
+    xc = np.zeros_like(x); vc = np.zeros_like(v)
+    a = accel(x)
+    vc += 0.5 * a * dt
+    tv = v.copy(); v = tv + vc; vc += tv - v
+    es = []
+    if energy is not None and every:
+        es.append(energy(x, v - 0.5 * a * dt))
+    for s in range(1, nsteps + 1):
+        xc += v * dt
+        tx = x.copy(); x = tx + xc; xc += tx - x
+        a = accel(x)
+        vc += a * dt
+        tv = v.copy(); v = tv + vc; vc += tv - v
+        if energy is not None and every and s % every == 0:
+            es.append(energy(x, v - 0.5 * a * dt))
+    return x, v - 0.5 * a * dt, np.array(es)

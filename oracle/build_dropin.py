@@ -1,0 +1,60 @@
+"""Build oracle/_ref/libgrav_sim_dropin.so: the reference's libgrav_sim with its acceleration path replaced
+by ours.  TEST INFRASTRUCTURE (end-to-end integration tests through the reference's own integrators and
+Python-facing entry points); needs /root/reference, so it only runs in the build container -- the GPU box
+uses the prebuilt file.
+
+Composition (exactly what INTEGRATION.md tells a maintainer to do):
+  * every reference source file EXCEPT src/acceleration.c, src/acceleration_barnes_hut.c, src/linear_octree.c,
+    compiled from where it lies, unmodified, with the project's flags;
+  * gravity-simulator_b200/csrc/grav_sim_shim.c compiled against the reference's own headers
+    (-DGRAV_SIM_USE_REFERENCE_HEADERS) in their place;
+  * src/integrator_whfast.c with a ONE-LINE patch: its static dispatcher whfast_acceleration() forwards to
+    grav_b200_shim_whfast_acceleration().  The patched text lives only in a temporary directory.
+  * linked against libgrav_b200.so.
+"""
+import re
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent
+REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+PKG = ROOT / "gravity-simulator_b200"
+OUT = HERE / "_ref" / "libgrav_sim_dropin.so"
+
+KEEP = ["cosmology.c", "error.c", "grav_sim.c", "integrator.c", "integrator_rk_embedded.c", "integrator_ias15.c",
+        "math_functions.c", "output.c", "progress_bar.c", "python_interface.c", "settings.c", "system.c", "utils.c"]
+FLAGS = ["-std=gnu99", "-O3", "-fPIC", "-fopenmp", "-DUSE_OPENMP", '-DVERSION_INFO="0.0.4-b200"', f"-I{REF}/src", f"-I{REF}/pcg", "-w"]
+
+
+def main():
+    if not (REF / "src").is_dir():
+        print(f"{REF} absent: keeping prebuilt {OUT.name} (if any)")
+        return
+    if not (PKG / "libgrav_b200.so").exists():
+        raise SystemExit("build gravity-simulator_b200/libgrav_b200.so first")
+    OUT.parent.mkdir(exist_ok=True)
+    src = (REF / "src" / "integrator_whfast.c").read_text()
+    # the definition (not the prototype) of the static dispatcher: ") {" follows the parameter list
+    m = re.search(r"IN_FILE ErrorStatus whfast_acceleration\(\s*double \*restrict a,[^)]*\)\s*\{", src)
+    if not m:
+        raise SystemExit("could not locate whfast_acceleration() in the reference")
+    hook = ("\n    extern ErrorStatus grav_b200_shim_whfast_acceleration(double *restrict, const System *, const double *restrict,"
+            " const double *restrict, const AccelerationParam *);\n"
+            "    return grav_b200_shim_whfast_acceleration(a, system, jacobi_x, eta, acceleration_param);\n")
+    patched = src[:m.end()] + hook + src[m.end():]
+    with tempfile.TemporaryDirectory() as tmp:
+        pw = Path(tmp) / "integrator_whfast_patched.c"
+        pw.write_text(patched)
+        cmd = (["/usr/bin/gcc"] + FLAGS + ["-shared", "-o", str(OUT)] + [str(REF / "src" / f) for f in KEEP]
+               + [str(pw), str(REF / "pcg" / "pcg_basic.c")]
+               + ["-DGRAV_SIM_USE_REFERENCE_HEADERS", f"-I{ROOT}/include", str(PKG / "csrc" / "grav_sim_shim.c")]
+               + [f"-L{PKG}", "-lgrav_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../gravity-simulator_b200", "-lm", "-lrt"])
+        subprocess.run(cmd, check=True)
+    print(f"built {OUT}")
+
+
+if __name__ == "__main__":
+    main()

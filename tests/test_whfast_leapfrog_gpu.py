@@ -1,0 +1,169 @@
+"""GPU parity: WHFast Jacobi-coordinate kernels (config 3), the device-resident leapfrog and the energy
+diagnostic (configs 2 and 4), and the drop-in library driven through the reference's own integrators."""
+import numpy as np
+import pytest
+
+from conftest import max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- WHFast kernels ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["whfast_solar", "whfast_belt"])
+def test_whfast_matches_golden(gb, golden, case):
+    g = golden(case)
+    for key in [k for k in g.files if k.startswith("a_whfast_")]:
+        method = key.split("_")[2]
+        eps = float(key.split("eps")[1])
+        a0 = np.full_like(g["x"], 7.25)       # entries the reference never writes keep the caller's values
+        a = gb.whfast_acceleration(g["x"], g["m"], float(g["G"]), g["jacobi_x"], g["eta"], method, eps, a0=a0)
+        ref = g[key].copy()
+        assert np.array_equal(a[1:], ref[1:]), (case, key, max_rel_err(a[1:], ref[1:]))   # same ops, same order: bit-exact
+        assert np.array_equal(a[0], a0[0])
+
+
+def test_whfast_vs_oracle_large_belt(gb, oracle, ics):
+    """Kirkwood-gap scale: Sun + 8 planets + 1e5 massless asteroids, sorted by distance as WHFast keeps them."""
+    from oracle.bind import jacobi_inputs
+    xs, vs, ms, G = ics.solar_system()
+    rng = np.random.default_rng(11)
+    k = 100000
+    r = rng.uniform(2.0, 3.35, k); ph = rng.uniform(0, 2 * np.pi, k)
+    belt = np.stack([r * np.cos(ph), r * np.sin(ph), rng.normal(0, 0.1, k)], axis=1) + xs[0]
+    order = np.argsort(np.concatenate([np.linalg.norm(xs[1:] - xs[0], axis=1), np.linalg.norm(belt - xs[0], axis=1)]))
+    x = np.concatenate([xs[:1], np.concatenate([xs[1:], belt])[order]])
+    m = np.concatenate([ms[:1], np.concatenate([ms[1:], np.zeros(k)])[order]])
+    jx, eta = jacobi_inputs(x, m)
+    a = gb.whfast_acceleration(x, m, G, jx, eta, "massless", 0.0)
+    ref = oracle.whfast_acceleration(x, m, G, jx, eta, "massless", 0.0)
+    assert np.array_equal(a[1:], ref[1:])
+    # and the all-massive O(N^3) variant on a small system
+    x9, m9 = xs, ms
+    jx9, eta9 = jacobi_inputs(x9, m9)
+    assert np.array_equal(gb.whfast_acceleration(x9, m9, G, jx9, eta9, "pairwise", 0.01)[1:],
+                          oracle.whfast_acceleration(x9, m9, G, jx9, eta9, "pairwise", 0.01)[1:])
+
+
+def test_whfast_rejects_barnes_hut(gb, ics):
+    xs, vs, ms, G = ics.solar_system()
+    with pytest.raises(gb.GravB200Error, match="Only pairwise and massless"):
+        gb.whfast_acceleration(xs, ms, G, xs, np.cumsum(ms), "barnes_hut")
+
+
+# ---- device-resident leapfrog + energy ----------------------------------------------------------------------
+def test_energy_matches_reference(gb, reference, ics):
+    x, v, m, G = ics.plummer(4096, 3)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        e = c.energy()
+    e_ref = reference.energy(x, v, m, G)
+    assert abs(e - e_ref) <= 1e-12 * abs(e_ref)
+
+
+def test_leapfrog_barnes_hut_trajectory_is_bit_identical(gb, reference, ics):
+    """Config 4 (scaled): two Plummer spheres, BH theta=0.5, eps=0.  BH accelerations are bit-identical to the
+    reference and the update kernels use its exact operation order, so the whole trajectory is."""
+    from oracle.bind import leapfrog_reference_loop
+    x, v, m, G = ics.two_plummer(1500, seed=5)
+    dt, steps = 1e-3, 40
+    acc = lambda xx: reference.acceleration(xx, m, G, "barnes_hut", 0.0, 0.5, 1)
+    xr, vr, _ = leapfrog_reference_loop(acc, x, v, m, G, dt, steps)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.leapfrog_begin(dt, "barnes_hut", 0.0, 0.5, 1)
+        c.leapfrog_steps(dt, steps)
+        assert np.array_equal(c.positions(), xr)
+        assert np.array_equal(c.velocities(), vr)       # snapshot convention while running
+        c.leapfrog_end()
+        assert np.array_equal(c.velocities(), vr)       # same values after the final synchronisation
+
+
+def test_leapfrog_direct_sum_energy_curve(gb, reference, ics):
+    """Config 2 (scaled to N=2048 so the CPU reference loop stays quick): softened Plummer sphere, dt=1e-3.
+    Gate from SURVEY.md section 8d: |dE/E0|(t) of GPU and reference agree to 1e-10 absolute."""
+    from oracle.bind import leapfrog_reference_loop
+    x, v, m, G = ics.plummer(2048, 8)
+    dt, steps, every, eps = 1e-3, 200, 10, 0.01
+    acc = lambda xx: reference.acceleration(xx, m, G, "pairwise", eps)
+    en = lambda xx, vv: reference.energy(xx, vv, m, G)
+    xr, vr, er = leapfrog_reference_loop(acc, x, v, m, G, dt, steps, en, every)
+    eg = []
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.leapfrog_begin(dt, "pairwise", eps)
+        eg.append(c.energy())
+        for _ in range(steps // every):
+            c.leapfrog_steps(dt, every)
+            eg.append(c.energy())
+        xg, vg = c.positions(), c.velocities()
+    eg = np.array(eg)
+    curve_g, curve_r = np.abs((eg - eg[0]) / eg[0]), np.abs((er - er[0]) / er[0])
+    assert np.max(np.abs(curve_g - curve_r)) <= 1e-10
+    assert curve_r.max() > 0          # the curve is not trivially flat
+    assert max_rel_err(xg, xr) <= 1e-10 and max_rel_err(vg, vr) <= 1e-9
+
+
+def test_leapfrog_config2_full_size_conserves_energy(gb, ics):
+    """Config 2 at full size (N=16384, eps=0.01, dt=1e-3): 100 device-resident steps; energy is conserved to the
+    level a second-order symplectic scheme gives at this step size, and the state never leaves the GPU."""
+    x, v, m, G = ics.plummer(16384, 2)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.leapfrog_begin(1e-3, "pairwise", 0.01)
+        e0 = c.energy()
+        c.leapfrog_steps(1e-3, 100)
+        e1 = c.energy()
+    assert abs((e1 - e0) / e0) < 1e-5
+
+
+# ---- the drop-in library under the reference's own integrators ---------------------------------------------
+def _dropin():
+    from oracle.bind import DROPIN_SO, REF_SO
+    if not (DROPIN_SO.exists() and REF_SO.exists()):
+        pytest.skip("oracle/_ref drop-in / reference builds not present")
+    return DROPIN_SO, REF_SO
+
+
+def test_dropin_leapfrog_barnes_hut_identical_to_reference(ics):
+    """launch_simulation_python of the reference build vs the same entry point of the drop-in build (reference
+    integrator code + our acceleration path): identical final state, bit for bit."""
+    from oracle.bind import launch_simulation
+    dropin, ref = _dropin()
+    x, v, m, G = ics.two_plummer(1000, seed=9)
+    kw = dict(tf=0.03, integrator="leapfrog", dt=1e-3, method="barnes_hut", softening_length=0.0, opening_angle=0.5)
+    xr, vr = launch_simulation(ref, x, v, m, G, **kw)
+    xd, vd = launch_simulation(dropin, x, v, m, G, **kw)
+    assert np.array_equal(xd, xr) and np.array_equal(vd, vr)
+
+
+def test_dropin_ias15_solar_system(ics, reference):
+    """Config 1 (shortened to 3 years so the ~2e4 tiny GPU force calls stay quick): IAS15, tolerance 1e-9, pairwise.
+    Final state and relative energy error agree with the reference run."""
+    from oracle.bind import launch_simulation
+    dropin, ref = _dropin()
+    x, v, m, G = ics.solar_system()
+    kw = dict(tf=3 * 365.24, integrator="ias15", tolerance=1e-9, method="pairwise")
+    xr, vr = launch_simulation(ref, x, v, m, G, **kw)
+    xd, vd = launch_simulation(dropin, x, v, m, G, **kw)
+    assert max_rel_err(xd, xr) <= 1e-9 and max_rel_err(vd, vr) <= 1e-9
+    e0 = reference.energy(x, v, m, G)
+    er, ed = reference.energy(xr, vr, m, G), reference.energy(xd, vd, m, G)
+    assert abs((er - e0) / e0) < 1e-12 and abs((ed - e0) / e0) < 1e-12
+
+
+def test_dropin_whfast_massless_belt(ics):
+    """Config 3 (scaled): WHFast + massless through the drop-in; the patched dispatcher forwards to the GPU kernel."""
+    from oracle.bind import launch_simulation
+    dropin, ref = _dropin()
+    xs, vs, ms, G = ics.solar_system()
+    rng = np.random.default_rng(2)
+    k = 500
+    a = rng.uniform(2.0, 3.35, k); ph = rng.uniform(0, 2 * np.pi, k)
+    pos = np.stack([a * np.cos(ph), a * np.sin(ph), np.zeros(k)], axis=1)
+    vc = np.sqrt(G * ms[0] / a)
+    vel = np.stack([-vc * np.sin(ph), vc * np.cos(ph), np.zeros(k)], axis=1)
+    x = np.concatenate([xs, pos + xs[0]]); v = np.concatenate([vs, vel + vs[0]]); m = np.concatenate([ms, np.zeros(k)])
+    kw = dict(tf=180.0 * 20, integrator="whfast", dt=180.0, method="massless")
+    xr, vr = launch_simulation(ref, x, v, m, G, **kw)
+    xd, vd = launch_simulation(dropin, x, v, m, G, **kw)
+    assert np.array_equal(xd, xr) and np.array_equal(vd, vr)

@@ -38,6 +38,7 @@ UNIT = "G interactions/s"
 FLOP_PER_INTERACTION = 20      # GPU-Gems-3 convention: 18 + rsqrt counted as 2
 FP64_OPS_PER_INTERACTION = 16  # FP64-pipe instructions our kernel actually issues per interaction
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12   # 37.2, used only if the live measurement fails
+NCU_DRAM_BYTES_PER_LAUNCH = 34179840 + 5368576   # dram read + write, profiles/r1_direct_sum_n1m.txt
 
 
 def parse_args():
@@ -260,8 +261,12 @@ def run_b200_arm(args):
     ach_tf = FLOP_PER_INTERACTION * k_inter / (k_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-        "traffic": None, "kernel": "direct_sum_kernel<2,false>", "kernel_ms": k_ms,
-        "convention": f"{FLOP_PER_INTERACTION} flop per ordered interaction; peak = {peak_src} at {peak_mhz:.0f} MHz",
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and n == (1 << 20)) else None,
+        "traffic_note": "dram__bytes_read+write of one launch at N=2^20, ncu --set full (profiles/r1_direct_sum_n1m.txt); "
+                        "algorithmic bytes = 32 B x N sources + 24 B x N results = 58.7 MB",
+        "kernel": "direct_sum_kernel<4,false,false> (+ fix-up and special-tile kernels, <0.5% of the stage)", "kernel_ms": k_ms,
+        "convention": f"{FLOP_PER_INTERACTION} flop per ordered interaction; peak = {peak_src} "
+                      f"(= {peak_mhz:.0f} MHz x 148 SM x 64 DFMA lanes x 2)",
         "fp64_pipe_util": FP64_OPS_PER_INTERACTION * k_inter / (k_ms * 1e-3) / (peak_tf * 1e12 / 2.0),
         "fp64_pipe_util_note": f"{FP64_OPS_PER_INTERACTION} FP64-pipe instructions per interaction over the measured DFMA issue rate",
     }

@@ -62,8 +62,9 @@ extern "C" int grav_b200_measure_fp64_peak(int device, double *tflops, double *s
     }
     const double fmas = (double)grid * 256.0 * PEAK_CHAINS * 4.0 * PEAK_ITERS;
     *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
-    // clock estimate: block 0's cycle count over the kernel duration (it runs for ~the whole kernel)
-    if (sm_mhz) *sm_mhz = (double)cyc / (best * 1e-3) / 1e6;
+    // equivalent SM clock if every SM retires 64 DFMA per cycle (clock64() does not tick at the SM clock here)
+    (void)cyc;
+    if (sm_mhz) *sm_mhz = *tflops * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) / 1e6;
     cudaFree(d_out);
     cudaFree(d_clk);
     cudaEventDestroy(e0);

@@ -135,19 +135,19 @@ direct_sum_kernel(const DSArgs p)
     __shared__ double tile_altm[MASSLESS ? DS_TJ : 1];
 
     const int tid = threadIdx.x;
+    // unit range of this CTA (64-bit only for the product c*U; U itself fits in 32 bits for N <= 2^24)
     const long long U = (long long)p.NB * p.NT;
-    const long long C = gridDim.x;
-    const long long u0 = unit_begin(blockIdx.x, U, C);
-    const long long u1 = unit_begin(blockIdx.x + 1, U, C);
+    const int u0 = (int)unit_begin(blockIdx.x, U, gridDim.x);
+    const int u1 = (int)unit_begin(blockIdx.x + 1, U, gridDim.x);
     if (u0 >= u1) return;
-    const int ib_first = (int)(u0 / p.NT);
+    const int ib_first = u0 / p.NT;
 
-    long long u = u0;
+    int u = u0;
     while (u < u1) {
-        const int ib = (int)(u / p.NT);
-        const int jt0 = (int)(u - (long long)ib * p.NT);
-        const long long seg_end = min(u1, (long long)(ib + 1) * p.NT);
-        const int jt1 = (int)(seg_end - (long long)ib * p.NT);
+        const int ib = u / p.NT;
+        const int jt0 = u - ib * p.NT;
+        const int seg_end = min(u1, (ib + 1) * p.NT);
+        const int jt1 = seg_end - ib * p.NT;
         const bool full = (jt0 == 0 && jt1 == p.NT);
 
         // targets of this thread
@@ -159,7 +159,7 @@ direct_sum_kernel(const DSArgs p)
 #pragma unroll
         for (int t = 0; t < TI; t++) {
             const int i = blk_lo + t * DS_BLOCK + tid;
-            ii[t] = i;
+            ii[t] = (CHECK || MASSLESS) ? i : 0;     // only the checked loop needs the ids kept live
             const double4 q = (i < p.i_hi) ? p.tgt[i] : make_double4(0.0, 0.0, 0.0, 1.0);
             xi[t] = q.x; yi[t] = q.y; zi[t] = q.z;
             alt[t] = MASSLESS ? (q.w == 0.0) : false;
@@ -183,7 +183,7 @@ direct_sum_kernel(const DSArgs p)
         if (full) {
 #pragma unroll
             for (int t = 0; t < TI; t++) {
-                const int i = ii[t];
+                const int i = blk_lo + t * DS_BLOCK + tid;
                 if (i < p.i_hi) {
                     // a_i = -G * sum (x_i - x_j) s = G * sum (x_j - x_i) s
                     p.acc[3 * (size_t)i + 0] = p.G * a.x[t];

@@ -115,7 +115,8 @@ _libs = None
 
 
 def lib_paths():
-    return HERE / "libgrav_b200.so", HERE / "libgrav_sim_b200.so"
+    # GRAV_B200_LIB: alternative build of the CUDA library (kernel tuning experiments only)
+    return Path(os.environ.get("GRAV_B200_LIB", HERE / "libgrav_b200.so")), HERE / "libgrav_sim_b200.so"
 
 
 def load():

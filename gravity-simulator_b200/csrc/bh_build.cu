@@ -206,11 +206,18 @@ __global__ void __launch_bounds__(256) walk_nodes_kernel(int M, const int *__res
     w->cx = cx[id]; w->cy = cy[id]; w->cz = cz[id];
     w->kq = fixed_mode ? K[f] : K[perm[f]];
     w->fc = nchild[id] > 0 ? fc[id] : -1;
-    w->count = np[id];
-    w->mass = mass[id];
     w->first = f;
+    w->mass = mass[id];
     w->pad = 0;
-    if (id == 0) { w->next = -1; w->level = 0; }
+    // next / level_count of every other node are written by rope_kernel (launched after this kernel)
+    if (id == 0) { w->next = -1; w->level_count = np[id]; }
+}
+
+__global__ void __launch_bounds__(256) gather_sorted_kernel(const double4 *__restrict__ posm, const int *__restrict__ perm, int n,
+                                                           double4 *__restrict__ out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) out[p] = posm[perm[p]];
 }
 
 // Ropes, one level at a time from the root down: the last child inherits its parent's rope.
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(256) rope_kernel(const ExpRec *__restrict__ re
     for (int k = 0; k < r.nch; k++) {
         const int cid = r.first_child + k;
         nodes[cid].next = (k < r.nch - 1) ? cid + 1 : my_next;
-        nodes[cid].level = r.level + 1;
+        nodes[cid].level_count = ((r.level + 1) << WALK_COUNT_BITS) | (r.b[k + 1] - r.b[k]);
     }
 }
 
@@ -364,6 +371,10 @@ int bh_pack_walk_nodes(grav_b200_ctx *c)
                                                             t.node_fc.as<int>(), t.node_mass.as<double>(), t.node_cx.as<double>(),
                                                             t.node_cy.as<double>(), t.node_cz.as<double>(), t.keys.as<long long>(),
                                                             t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0, nodes);
+    GB_LAUNCH_CHECK();
+    count_launch();
+    GB_TRY(t.posm_sorted.reserve(sizeof(double4) * (size_t)t.n));
+    gather_sorted_kernel<<<(t.n + 255) / 256, 256, 0, c->stream>>>(c->posm.as<double4>(), t.perm.as<int>(), t.n, t.posm_sorted.as<double4>());
     GB_LAUNCH_CHECK();
     count_launch();
     for (int l = 0; l < t.max_level; l++) {

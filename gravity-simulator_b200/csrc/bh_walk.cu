@@ -8,10 +8,15 @@
 // a rope (`next`, the node that follows in depth-first order when the subtree is skipped), so a visit is
 //     accept or leaf  ->  node = next          open  ->  node = first child
 // and each lane advances through exactly the nodes, in exactly the order, the reference visits for that
-// particle.  A first version shared one traversal per warp (union of the lanes' trees, per-lane masks); the ncu
-// profile (profiles/r1_walk_warp_union.txt) showed it issue-bound with 7 of 32 lanes active in the accept path
-// and 4.4x more node visits than a single particle needs, because the opening test separates Morton
-// neighbours.  Independent lanes remove both costs.
+// particle.  History (ncu evidence under profiles/):
+//   r1_walk_warp_union        one traversal per warp with lane masks: issue-bound, 7/32 lanes in the accept
+//                             path, 4.4x the node visits one particle needs                     67.5 ms
+//   r1_walk_stackless_exact   independent lanes + ropes: half the executed instructions          41.7 ms
+//   r1_walk_state_machine     one item per trip; still ran a 3-load leaf path for 2/32 lanes in 77 % of trips
+//   (this version)            accepted nodes and leaf particles share ONE source path: a source is a packed
+//                             (x,y,z,m) record -- the node's (com, mass) or the particle's record from a
+//                             Morton-sorted copy -- so the self test is a position compare and no lane waits
+//                             on a perm -> posm chain                                   (N=2^20 Plummer, 1 GPU)
 //
 // All arithmetic that feeds a decision or the result uses IEEE operations without FMA contraction
 // (__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn) in the reference's order, so in reference mode the output is
@@ -28,18 +33,30 @@ namespace gb {
 
 constexpr int MAX_LEVEL = 21;
 constexpr int WALK_BLOCK = 128;
-constexpr int WALK_POOL = WALK_BLOCK;       // targets per CTA; > WALK_BLOCK enables per-lane work fetching (measured slower: 46 vs 41 ms, N=2^20 Plummer)
+// Tuning knobs kept for A/B builds (measured at N=2^20 Plummer, reference mode):
+//   WALK_VARIANT 0  next node's record prefetched into registers before the arithmetic        39.3 ms  <- default
+//   WALK_VARIANT 1  prefetch.global.L1 + reload at loop top (12 fewer live registers)          41.9 ms
+//   WALK_MINB 10/12 (48/40 registers, more resident warps)                                41.6 / 50.7 ms
+// More occupancy does not help: the kernel is bound by instructions per item and lane divergence, not latency.
+#ifndef WALK_VARIANT
+#define WALK_VARIANT 0
+#endif
+#ifndef WALK_MINB
+#define WALK_MINB 8
+#endif
 
 struct WalkArgs {
     const WalkNode *nodes;
-    const long long *K;      // sorted keys
-    const int *perm;         // sorted position -> particle id
-    const double4 *posm;
-    int p_lo, p_hi;          // sorted positions handled by this launch
+    const long long *K;        // sorted keys
+    const int *perm;           // sorted position -> particle id
+    const double4 *psorted;    // particle records in sorted order
+    int p_lo, p_hi;            // sorted positions handled by this launch
     double G, eps2, theta2;
     double cell2[MAX_LEVEL + 2];   // (box_length / (2 << level))^2 per child level
-    double *acc;             // AoS [3n] by particle id
+    double *acc;               // AoS [3n] by particle id
 };
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct NodeRec {   // the 48 bytes of a WalkNode every visit needs, as loaded (three 16-byte read-only loads)
     int4 A, B, C;
@@ -53,104 +70,110 @@ __device__ __forceinline__ NodeRec load_rec(const WalkNode *nodes, int node)
 }
 
 // Per-lane state machine.  Each trip of the loop handles ONE item for the lane -- a node visit, or the next
-// particle of a leaf that is being summed directly -- in three steps that are the same code for every lane:
-//   decide    opening test on the current node record -> the next node id, and possibly a source (R, d2, m)
-//   prefetch  the record of the next node is requested BEFORE the arithmetic below, so its L1/L2 latency
-//             overlaps the sqrt/div sequence
-//   evaluate  f = G m / r^3 and the three accumulator updates, shared by accepted nodes and leaf particles
-//             (both are sqrt(((rx^2+ry^2)+rz^2)+eps^2) in the reference, :164-171 and :198-213)
+// particle of a leaf that is being summed directly -- in steps that are the same code for every lane:
+//   decide    opening test on the current node record -> the next node id, and whether there is a source
+//   fetch     the next node's record is requested BEFORE the arithmetic below (its latency overlaps the sqrt/div);
+//             the source's mass (accepted node) or record (leaf particle) is loaded
+//   evaluate  R = x_i - x_src, f = G m / r^3 and the three accumulator updates: sqrt(((rx^2+ry^2)+rz^2)+eps^2) for
+//             both kinds of source, as in the reference (:164-171 and :198-213)
 template <bool FIXED>
-__global__ void __launch_bounds__(WALK_BLOCK) walk_kernel(const WalkArgs a)
+__global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkArgs a)
 {
     __shared__ double s_cell2[MAX_LEVEL + 2];
-    __shared__ int s_next;   // next unclaimed target of this CTA's pool
     if (threadIdx.x < MAX_LEVEL + 2) s_cell2[threadIdx.x] = a.cell2[threadIdx.x];
-    // Work distribution: a CTA owns a pool of WALK_POOL Morton-consecutive targets.  A lane that finishes its
-    // particle claims the next one of the pool (shared-memory counter), so lanes with short walks do not idle
-    // behind lanes with long ones.  In reference mode walk lengths differ wildly even between Morton
-    // neighbours, because the inclusion test uses an unrelated particle's key (see file header).
-    const int pool_lo = a.p_lo + blockIdx.x * WALK_POOL;
-    const int pool_hi = min(pool_lo + WALK_POOL, a.p_hi);
-    if (threadIdx.x == 0) s_next = pool_lo + WALK_BLOCK;
     __syncthreads();
-    int p = pool_lo + threadIdx.x;
-    const int root_fc = __ldg(&a.nodes[0].fc);   // the root is always expanded
+    const int p = a.p_lo + blockIdx.x * WALK_BLOCK + threadIdx.x;
+    if (p >= a.p_hi) return;
+    const int idx = a.perm[p];
+    const double4 me = a.psorted[p];
+    const double xi = me.x, yi = me.y, zi = me.z;
+    const long long ki = FIXED ? a.K[p] : a.K[idx];
+    double ax = 0.0, ay = 0.0, az = 0.0;
 
-    while (p < pool_hi) {
-        const int idx = a.perm[p];
-        const double4 me = a.posm[idx];
-        const double xi = me.x, yi = me.y, zi = me.z;
-        const long long ki = FIXED ? a.K[p] : a.K[idx];
-        double ax = 0.0, ay = 0.0, az = 0.0;
-
-        int node = root_fc;
-        NodeRec rec = load_rec(a.nodes, node);
-        int leaf_pos = 0, leaf_rem = 0, leaf_next = -1;
-        while (node >= 0) {
-            bool have = false;
-            double rx = 0.0, ry = 0.0, rz = 0.0, d2 = 0.0, msrc = 0.0;
-            int new_node = node;
-            if (leaf_rem == 0) {
-                const double cx = __hiloint2double(rec.A.y, rec.A.x), cy = __hiloint2double(rec.A.w, rec.A.z);
-                const double cz = __hiloint2double(rec.B.y, rec.B.x);
-                const long long kq = ((long long)rec.B.w << 32) | (unsigned)rec.B.z;
-                const int fc = rec.C.x, next = rec.C.y, level = rec.C.z, count = rec.C.w;
-                const int shift = 3 * (MAX_LEVEL - level);
-                const bool leaf = fc < 0;
-                const bool inside = ((ki ^ kq) >> shift) == 0;
-                bool accepted = false;
-                if (FIXED ? (!inside && !leaf) : !inside) {
-                    rx = __dsub_rn(xi, cx); ry = __dsub_rn(yi, cy); rz = __dsub_rn(zi, cz);
-                    d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                    accepted = s_cell2[level] < __dmul_rn(a.theta2, d2);
-                }
-                if (accepted) {
-                    msrc = __ldg(&a.nodes[node].mass);
-                    have = true;
-                    new_node = next;
-                } else if (leaf) {
-                    leaf_pos = __ldg(&a.nodes[node].first);
-                    leaf_rem = count;
-                    leaf_next = next;
-                } else {
-                    new_node = fc;
-                }
+    int node = __ldg(&a.nodes[0].fc);   // the root is always expanded
+#if WALK_VARIANT == 0
+    NodeRec rec = load_rec(a.nodes, node);
+#endif
+    int leaf_pos = 0, leaf_rem = 0, leaf_next = -1;
+    while (node >= 0) {
+#if WALK_VARIANT == 1
+        const NodeRec rec = load_rec(a.nodes, node);
+#endif
+        bool have = false;              // this trip produced a source
+        bool from_node = false;         // ... which is the current node (else: particle at sorted position src_pos)
+        int src_pos = 0;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        int new_node = node;
+        if (leaf_rem == 0) {
+            const double cx = __hiloint2double(rec.A.y, rec.A.x), cy = __hiloint2double(rec.A.w, rec.A.z);
+            const double cz = __hiloint2double(rec.B.y, rec.B.x);
+            const long long kq = ((long long)rec.B.w << 32) | (unsigned)rec.B.z;
+            const int fc = rec.C.x, next = rec.C.y, first = rec.C.z;
+            const int level = rec.C.w >> WALK_COUNT_BITS, count = rec.C.w & ((1 << WALK_COUNT_BITS) - 1);
+            const int shift = 3 * (MAX_LEVEL - level);
+            const bool leaf = fc < 0;
+            const bool inside = ((ki ^ kq) >> shift) == 0;
+            bool accepted = false;
+            if (FIXED ? (!inside && !leaf) : !inside) {
+                const double rx = __dsub_rn(xi, cx), ry = __dsub_rn(yi, cy), rz = __dsub_rn(zi, cz);
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                accepted = s_cell2[level] < __dmul_rn(a.theta2, d2);
             }
-            if (leaf_rem > 0) {   // one particle of the leaf per trip (sorted order), skipping the target itself
-                const int jdx = __ldg(a.perm + leaf_pos);
-                leaf_pos++;
-                leaf_rem--;
-                if (jdx != idx) {
-                    const double4 pj = a.posm[jdx];
-                    rx = __dsub_rn(xi, pj.x); ry = __dsub_rn(yi, pj.y); rz = __dsub_rn(zi, pj.z);
-                    d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                    msrc = pj.w;
-                    have = true;
-                }
-                if (leaf_rem == 0) new_node = leaf_next;
-            }
-            if (new_node != node && new_node >= 0) rec = load_rec(a.nodes, new_node);
-            node = new_node;
-            if (have) {
-                const double s = __dadd_rn(d2, a.eps2);
-                const double gm = __dmul_rn(a.G, msrc);
-                double f;
-                if (gm == 0.0 && s > 1e-200 && s < 1e200) {
-                    f = gm;     // 0 / r^3 with r^3 finite and positive: exactly the signed zero gm (dropped zero-mass leaves)
-                } else {
-                    const double r = __dsqrt_rn(s);
-                    f = __ddiv_rn(gm, __dmul_rn(__dmul_rn(r, r), r));
-                }
-                ax = __dsub_rn(ax, __dmul_rn(f, rx));
-                ay = __dsub_rn(ay, __dmul_rn(f, ry));
-                az = __dsub_rn(az, __dmul_rn(f, rz));
+            if (accepted) {
+                have = true; from_node = true;
+                sx = cx; sy = cy; sz = cz;
+                new_node = next;
+            } else if (leaf) {
+                leaf_pos = first;
+                leaf_rem = count;
+                leaf_next = next;
+            } else {
+                new_node = fc;
             }
         }
-        a.acc[3 * (size_t)idx + 0] = ax;
-        a.acc[3 * (size_t)idx + 1] = ay;
-        a.acc[3 * (size_t)idx + 2] = az;
-        p = atomicAdd(&s_next, 1);
+        if (leaf_rem > 0) {   // one particle of the leaf per trip (sorted order), skipping the target itself
+            src_pos = leaf_pos;
+            have = (leaf_pos != p);
+            leaf_pos++;
+            leaf_rem--;
+            if (leaf_rem == 0) new_node = leaf_next;
+        }
+        // fetch: source data of this trip, then the next node's record
+        double msrc = 0.0;
+        if (have) {
+            if (from_node) {
+                msrc = __ldg(&a.nodes[node].mass);
+            } else {
+                const double4 q = a.psorted[src_pos];
+                sx = q.x; sy = q.y; sz = q.z; msrc = q.w;
+            }
+        }
+#if WALK_VARIANT == 0
+        if (new_node != node && new_node >= 0) rec = load_rec(a.nodes, new_node);
+#else
+        if (new_node != node && new_node >= 0) prefetch_l1(a.nodes + new_node);
+#endif
+        node = new_node;
+        if (have) {
+            const double rx = __dsub_rn(xi, sx), ry = __dsub_rn(yi, sy), rz = __dsub_rn(zi, sz);
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+            const double s = __dadd_rn(d2, a.eps2);
+            const double gm = __dmul_rn(a.G, msrc);
+            double f;
+            if (gm == 0.0 && s > 1e-200 && s < 1e200) {
+                f = gm;     // 0 / r^3 with r^3 finite and positive: exactly the signed zero gm (dropped zero-mass leaves)
+            } else {
+                const double r = __dsqrt_rn(s);
+                f = __ddiv_rn(gm, __dmul_rn(__dmul_rn(r, r), r));
+            }
+            ax = __dsub_rn(ax, __dmul_rn(f, rx));
+            ay = __dsub_rn(ay, __dmul_rn(f, ry));
+            az = __dsub_rn(az, __dmul_rn(f, rz));
+        }
     }
+    a.acc[3 * (size_t)idx + 0] = ax;
+    a.acc[3 * (size_t)idx + 1] = ay;
+    a.acc[3 * (size_t)idx + 2] = az;
 }
 
 int bh_pack_walk_nodes(grav_b200_ctx *c);
@@ -163,7 +186,7 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
     a.nodes = t.node_walk.as<WalkNode>();
     a.K = t.keys.as<long long>();
     a.perm = t.perm.as<int>();
-    a.posm = c->posm.as<double4>();
+    a.psorted = t.posm_sorted.as<double4>();
     // ranks share the walk by sorted position (Morton-contiguous), not by particle id
     a.p_lo = (int)(((long long)c->rank * c->n) / c->world);
     a.p_hi = (int)(((long long)(c->rank + 1) * c->n) / c->world);
@@ -179,7 +202,7 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
     if (c->world > 1) GB_CUDA(cudaMemsetAsync(a.acc, 0, sizeof(double) * 3 * (size_t)c->n, c->stream));
     const int npos = a.p_hi - a.p_lo;
     if (npos > 0) {
-        const int blocks = (npos + WALK_POOL - 1) / WALK_POOL;
+        const int blocks = (npos + WALK_BLOCK - 1) / WALK_BLOCK;
         if (c->bh_mode == GRAV_B200_BH_FIXED) walk_kernel<true><<<blocks, WALK_BLOCK, 0, c->stream>>>(a);
         else walk_kernel<false><<<blocks, WALK_BLOCK, 0, c->stream>>>(a);
         GB_LAUNCH_CHECK();

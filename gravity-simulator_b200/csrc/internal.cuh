@@ -48,7 +48,7 @@ struct DevBuf {
 enum { ST_TOTAL = 0, ST_GATHER = 1, ST_FORCE = 2, ST_MORTON = 3, ST_SORT = 4, ST_BUILD = 5, ST_COUNT = 6 };
 
 // What the tree walk reads per node: one 64-byte record.  The first 48 bytes are needed at every visit,
-// the last 16 only when the node is accepted (mass) or is a leaf that must be summed directly (first).
+// the mass only when the node is accepted.
 // `next` is the "rope": the node that follows in depth-first order when this node's subtree is skipped
 // (next sibling, else the parent's rope; -1 ends the walk), which makes the walk stackless.
 struct WalkNode {
@@ -56,12 +56,12 @@ struct WalkNode {
     long long kq;      // key the inclusion test compares against (mode dependent)
     int fc;            // id of the first child, -1 for a leaf
     int next;
-    int level;
-    int count;         // particles in the node
-    double mass;
     int first;         // sorted position of the node's first particle
-    int pad;
+    int level_count;   // level << 26 | particles in the node (N <= 2^24 < 2^26)
+    double mass;
+    long long pad;
 };
+constexpr int WALK_COUNT_BITS = 26;
 static_assert(sizeof(WalkNode) == 64, "WalkNode layout");
 
 // Device-side linear octree (layout in DESIGN.md "BH data layout")
@@ -83,6 +83,7 @@ struct DevTree {
     DevBuf node_mass, node_cx, node_cy, node_cz;        // double[num_nodes]
     DevBuf node_mtd;                        // double[3*num_nodes] mass-weighted position sums
     DevBuf node_walk;                       // packed 64-byte walk records
+    DevBuf posm_sorted;                     // double4[n]: posm in sorted (Morton) order, for the walk's leaf sums
     DevBuf ki;                              // int64[n] per-target walk key
     DevBuf counters;                        // misc device ints
 };

@@ -206,30 +206,27 @@ direct_sum_kernel(const DSArgs p)
     }
 }
 
-// The tiles the fast kernel skipped: for each target block, the (at most IB/DS_TJ + 1) source tiles that
-// overlap it plus the partial last tile, through the checked loop; acc += G * sum.  One CTA per block,
-// runs after the main kernel and its fix-up (same stream), so the result is deterministic.
-template <int TI>
-__global__ void __launch_bounds__(DS_BLOCK, 2) direct_sum_special_kernel(const DSArgs p)
+// The tiles the fast kernel skipped: for each of its target blocks (IB_MAIN targets), the source tiles that overlap
+// the block plus the partial last tile, through the checked loop; acc += G * sum.  One target per thread and one
+// CTA per 256 targets (4x the CTAs of the main decomposition, the same 4-5 tiles each); runs after the main kernel
+// and its fix-up on the same stream, so the result is deterministic.
+template <int IB_MAIN>
+__global__ void __launch_bounds__(DS_BLOCK) direct_sum_special_kernel(const DSArgs p)
 {
-    constexpr int IB = DS_BLOCK * TI;
     __shared__ double4 tile[DS_TJ];
-    const int tid = threadIdx.x, ib = blockIdx.x;
-    double xi[TI], yi[TI], zi[TI];
-    int ii[TI];
-    bool alt[TI];
-    Acc<TI> a;
-    const int blk_lo = p.i_lo + ib * IB;
-#pragma unroll
-    for (int t = 0; t < TI; t++) {
-        const int i = blk_lo + t * DS_BLOCK + tid;
-        ii[t] = i;
-        const double4 q = (i < p.i_hi) ? p.tgt[i] : make_double4(0.0, 0.0, 0.0, 1.0);
-        xi[t] = q.x; yi[t] = q.y; zi[t] = q.z;
-        alt[t] = false;
-        a.x[t] = 0.0; a.y[t] = 0.0; a.z[t] = 0.0;
-    }
-    const int blk_hi = min(blk_lo + IB, p.i_hi);
+    const int tid = threadIdx.x;
+    const int my_lo = p.i_lo + blockIdx.x * DS_BLOCK;
+    // the main-kernel block these targets belong to decides which tiles were skipped for them
+    const int blk_lo = p.i_lo + ((my_lo - p.i_lo) / IB_MAIN) * IB_MAIN;
+    const int blk_hi = min(blk_lo + IB_MAIN, p.i_hi);
+    double xi[1], yi[1], zi[1];
+    int ii[1];
+    bool alt[1] = {false};
+    Acc<1> a;
+    ii[0] = my_lo + tid;
+    const double4 q = (ii[0] < p.i_hi) ? p.tgt[ii[0]] : make_double4(0.0, 0.0, 0.0, 1.0);
+    xi[0] = q.x; yi[0] = q.y; zi[0] = q.z;
+    a.x[0] = 0.0; a.y[0] = 0.0; a.z[0] = 0.0;
     const int jt_a = blk_lo / DS_TJ, jt_b = min((blk_hi - 1) / DS_TJ, p.NT - 1);
     const int last = p.NT - 1;
     const bool last_partial = (p.n_src % DS_TJ) != 0 && last > jt_b;
@@ -238,16 +235,12 @@ __global__ void __launch_bounds__(DS_BLOCK, 2) direct_sum_special_kernel(const D
         __syncthreads();
         tile[tid] = p.src[(size_t)jt * DS_TJ + tid];
         __syncthreads();
-        tile_interactions<TI, true, false>(tile, nullptr, nullptr, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
+        tile_interactions<1, true, false>(tile, nullptr, nullptr, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
     }
-#pragma unroll
-    for (int t = 0; t < TI; t++) {
-        const int i = ii[t];
-        if (i < p.i_hi) {
-            p.acc[3 * (size_t)i + 0] += p.G * a.x[t];
-            p.acc[3 * (size_t)i + 1] += p.G * a.y[t];
-            p.acc[3 * (size_t)i + 2] += p.G * a.z[t];
-        }
+    if (ii[0] < p.i_hi) {
+        p.acc[3 * (size_t)ii[0] + 0] += p.G * a.x[0];
+        p.acc[3 * (size_t)ii[0] + 1] += p.G * a.y[0];
+        p.acc[3 * (size_t)ii[0] + 2] += p.G * a.z[0];
     }
 }
 
@@ -306,7 +299,8 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
     }
     // Small source counts (and the massless method) run everything through the checked loop in one kernel;
     // otherwise fast kernel + special-tile kernel.
-    const bool all_checked = MASSLESS || a.NT <= 64;
+    static const int checked_max_tiles = getenv("GRAV_B200_DS_CHECKED_TILES") ? atoi(getenv("GRAV_B200_DS_CHECKED_TILES")) : 64;
+    const bool all_checked = MASSLESS || a.NT <= checked_max_tiles;
     const long long U = (long long)a.NB * a.NT;
     long long grid = (long long)c->sm_count * 2;
     if (grid > U) grid = U;
@@ -325,7 +319,8 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
         count_launch();
     }
     if (!all_checked) {
-        direct_sum_special_kernel<TI><<<a.NB, DS_BLOCK, 0, c->stream>>>(a);
+        // one target per thread here: 4x the CTAs of the main decomposition, one or two tiles each
+        direct_sum_special_kernel<IB><<<(n_tgt + DS_BLOCK - 1) / DS_BLOCK, DS_BLOCK, 0, c->stream>>>(a);
         GB_LAUNCH_CHECK();
         count_launch();
     }

@@ -105,97 +105,174 @@ __global__ void __launch_bounds__(256) morton_kernel(const double4 *__restrict__
 }
 
 // ---- stable LSD radix sort of (key, index) pairs ------------------------------------------------------
-// Unit of work = one warp and a contiguous chunk of SORT_CHUNK pairs, processed 32 at a time in order.
-//   pass 1 (histogram): per chunk, count the 256 digit values          -> hist[digit][chunk]
-//   scan              : exclusive prefix sum over hist in (digit, chunk) order = first output slot of
-//                       every (digit, chunk) group
-//   pass 2 (scatter)  : per chunk, walk the pairs again in order; rank inside a group of 32 comes from
-//                       match.any + popc of lower lanes, the running count per digit lives in shared memory.
-// Within a digit value output order = chunk order, then position order: stable.
+// 8 passes of 8 bits.  A CTA of 256 threads owns a tile of 4096 consecutive pairs; warp w owns the contiguous
+// sub-chunk [512 w, 512 (w+1)) and walks it 32 pairs at a time, in order.
+//   pass A (sort_hist_kernel)    per tile: digit counts                       -> hist[digit][tile]
+//   scan                         exclusive prefix sum in (digit, tile) order  =  first output slot of each group
+//   pass B (sort_scatter_kernel) per tile: (1) per-warp digit counts (match.any, warp-private rows, no atomics),
+//                                (2) 256 threads turn them into local slots: exclusive over warps, then over digits,
+//                                (3) every pair is placed in shared memory at  slot = warp_start[w][d] + rank
+//                                    (rank = popc of lower lanes with the same digit) -- the tile is now sorted by
+//                                    digit, stably -- (4) thread i streams slot i to  gbase[d] + i : consecutive
+//                                    threads write consecutive addresses inside each digit run (avg 16 pairs).
+// Output order inside a digit value = tile order, then warp order, then position order: stable.
+int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);
 constexpr int SORT_BITS = 8;
 constexpr int SORT_RADIX = 1 << SORT_BITS;
-constexpr int SORT_CHUNK = 2048;        // pairs per warp
-constexpr int SORT_WARPS = 8;           // warps per CTA
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ROUNDS = 16;                              // pairs per thread
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;        // 4096 pairs per CTA
+constexpr int SORT_WCHUNK = 32 * SORT_ROUNDS;                // 512 pairs per warp
+constexpr size_t SORT_SMEM = (size_t)SORT_TILE * (sizeof(long long) + sizeof(int));   // staging: 48 KiB
 
-__global__ void __launch_bounds__(SORT_WARPS * 32) sort_hist_kernel(const long long *__restrict__ keys, int n, int shift,
-                                                                    int num_chunks, int *__restrict__ hist)
+__device__ __forceinline__ int digit_of(long long k, int shift) { return (int)((unsigned long long)k >> shift) & (SORT_RADIX - 1); }
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const long long *__restrict__ keys, int n, int shift,
+                                                                 int num_tiles, int *__restrict__ hist)
 {
-    __shared__ int cnt[SORT_WARPS][SORT_RADIX];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunk = blockIdx.x * SORT_WARPS + warp;
-    for (int d = lane; d < SORT_RADIX; d += 32) cnt[warp][d] = 0;
-    __syncwarp();
-    if (chunk < num_chunks) {
-        const int base = chunk * SORT_CHUNK;
-        const int end = min(base + SORT_CHUNK, n);
-        for (int p0 = base; p0 < end; p0 += 32) {
-            const int p = p0 + lane;
-            const bool valid = p < end;
-            const int d = valid ? ((int)((unsigned long long)keys[p] >> shift) & (SORT_RADIX - 1)) : SORT_RADIX;
-            const unsigned same = __match_any_sync(0xffffffffu, d);
-            if (valid && (same >> lane) == 1u) cnt[warp][d] += __popc(same);   // one lane per distinct digit
-            __syncwarp();
-        }
-        for (int d = lane; d < SORT_RADIX; d += 32) hist[(size_t)d * num_chunks + chunk] = cnt[warp][d];
+    __shared__ int cnt[SORT_RADIX];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * SORT_TILE;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const int p = base + r * SORT_THREADS + threadIdx.x;      // order is irrelevant for counting: coalesced
+        const bool valid = p < n;
+        const int d = valid ? digit_of(keys[p], shift) : SORT_RADIX;
+        const unsigned same = __match_any_sync(0xffffffffu, d);
+        if (valid && (same >> lane) == 1u) atomicAdd(&cnt[d], __popc(same));   // one atomic per distinct digit per warp
     }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * num_tiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(SORT_WARPS * 32) sort_scatter_kernel(const long long *__restrict__ keys_in,
-                                                                       const int *__restrict__ perm_in, int n, int shift,
-                                                                       int num_chunks, const int *__restrict__ offs,
-                                                                       long long *__restrict__ keys_out,
-                                                                       int *__restrict__ perm_out)
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const long long *__restrict__ keys_in,
+                                                                    const int *__restrict__ vals_in, int n, int shift,
+                                                                    int num_tiles, const int *__restrict__ offs,
+                                                                    long long *__restrict__ keys_out,
+                                                                    int *__restrict__ vals_out)
 {
-    __shared__ int pos[SORT_WARPS][SORT_RADIX];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunk = blockIdx.x * SORT_WARPS + warp;
-    if (chunk >= num_chunks) return;
-    for (int d = lane; d < SORT_RADIX; d += 32) pos[warp][d] = offs[(size_t)d * num_chunks + chunk];
-    __syncwarp();
-    const int base = chunk * SORT_CHUNK;
-    const int end = min(base + SORT_CHUNK, n);
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    long long *skeys = reinterpret_cast<long long *>(sort_smem);
+    int *svals = reinterpret_cast<int *>(sort_smem + (size_t)SORT_TILE * sizeof(long long));
+    __shared__ int wcnt[SORT_WARPS][SORT_RADIX];
+    __shared__ int gbase[SORT_RADIX];
+    __shared__ int wsum[SORT_WARPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned lt = (1u << lane) - 1u;
-    for (int p0 = base; p0 < end; p0 += 32) {
-        const int p = p0 + lane;
-        const bool valid = p < end;
-        long long k = 0;
-        int v = 0;
-        if (valid) { k = keys_in[p]; v = perm_in[p]; }
-        const int d = valid ? ((int)((unsigned long long)k >> shift) & (SORT_RADIX - 1)) : SORT_RADIX;   // invalid lanes never match
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        const unsigned same = __match_any_sync(0xffffffffu, d) & act;
-        int dst = 0;
-        if (valid) dst = pos[warp][d] + __popc(same & lt);
+    const int base = blockIdx.x * SORT_TILE;
+    const int tile_n = min(SORT_TILE, n - base);
+    for (int d = lane; d < SORT_RADIX; d += 32) wcnt[warp][d] = 0;
+
+    // (1) load this warp's sub-chunk in order and count digits
+    long long k[SORT_ROUNDS];
+    int v[SORT_ROUNDS];
+    const int wbase = warp * SORT_WCHUNK;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        k[r] = valid ? keys_in[base + li] : 0;
+        v[r] = valid ? vals_in[base + li] : 0;
+        const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
+        const unsigned same = __match_any_sync(0xffffffffu, d);
+        if (valid && (same >> lane) == 1u) wcnt[warp][d] += __popc(same);
         __syncwarp();
-        if (valid && (same >> lane) == 1u) pos[warp][d] += __popc(same);   // highest lane of each group advances the counter
+    }
+    __syncthreads();
+
+    // (2) local slots: thread d owns digit d
+    {
+        const int d = tid;
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            const int t = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += t;
+        }
+        // exclusive scan of the 256 digit totals
+        int inc = run;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) woff += (w < warp) ? wsum[w] : 0;
+        const int dstart = woff + inc - run;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) wcnt[w][d] += dstart;
+        gbase[d] = offs[(size_t)d * num_tiles + blockIdx.x] - dstart;
+    }
+    __syncthreads();
+
+    // (3) place every pair at its slot of the digit-sorted tile
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
+        const unsigned same = __match_any_sync(0xffffffffu, d);
+        if (valid) {
+            const int slot = wcnt[warp][d] + __popc(same & lt);
+            skeys[slot] = k[r];
+            svals[slot] = v[r];
+        }
         __syncwarp();
-        if (valid) { keys_out[dst] = k; perm_out[dst] = v; }
+        if (valid && (same >> lane) == 1u) wcnt[warp][d] += __popc(same);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // (4) stream the sorted tile out
+    for (int i = tid; i < tile_n; i += SORT_THREADS) {
+        const long long kk = skeys[i];
+        const int pos = gbase[digit_of(kk, shift)] + i;
+        keys_out[pos] = kk;
+        vals_out[pos] = svals[i];
     }
 }
 
-int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);
+// One stable pass on an 8-bit digit of arbitrary (key, value) arrays; scratch: t.hist / t.scan_tmp.
+int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift)
+{
+    DevTree &t = c->tree;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GB_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM));
+        attr_set = true;
+    }
+    const int num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    GB_TRY(t.hist.reserve(sizeof(int) * (size_t)SORT_RADIX * num_tiles));
+    sort_hist_kernel<<<num_tiles, SORT_THREADS, 0, c->stream>>>(kin, n, shift, num_tiles, t.hist.as<int>());
+    GB_LAUNCH_CHECK();
+    count_launch();
+    GB_TRY(exclusive_scan_int(c, t.hist.as<int>(), t.hist.as<int>(), SORT_RADIX * num_tiles, t.scan_tmp));
+    sort_scatter_kernel<<<num_tiles, SORT_THREADS, SORT_SMEM, c->stream>>>(kin, vin, n, shift, num_tiles, t.hist.as<int>(), kout, vout);
+    GB_LAUNCH_CHECK();
+    count_launch();
+    return GRAV_B200_OK;
+}
 
 // keys/perm sorted in place (8 passes ping-pong through keys_tmp/perm_tmp)
 int radix_sort_pairs(grav_b200_ctx *c)
 {
     DevTree &t = c->tree;
     const int n = t.n;
-    const int num_chunks = (n + SORT_CHUNK - 1) / SORT_CHUNK;
     GB_TRY(t.keys_tmp.reserve(sizeof(long long) * (size_t)n));
     GB_TRY(t.perm_tmp.reserve(sizeof(int) * (size_t)n));
-    GB_TRY(t.hist.reserve(sizeof(int) * (size_t)SORT_RADIX * num_chunks));
     long long *ka = t.keys.as<long long>(), *kb = t.keys_tmp.as<long long>();
     int *pa = t.perm.as<int>(), *pb = t.perm_tmp.as<int>();
-    const int blocks = (num_chunks + SORT_WARPS - 1) / SORT_WARPS;
     for (int pass = 0; pass < 8; pass++) {
-        const int shift = pass * SORT_BITS;
-        sort_hist_kernel<<<blocks, SORT_WARPS * 32, 0, c->stream>>>(ka, n, shift, num_chunks, t.hist.as<int>());
-        GB_LAUNCH_CHECK();
-        count_launch();
-        GB_TRY(exclusive_scan_int(c, t.hist.as<int>(), t.hist.as<int>(), SORT_RADIX * num_chunks, t.scan_tmp));
-        sort_scatter_kernel<<<blocks, SORT_WARPS * 32, 0, c->stream>>>(ka, pa, n, shift, num_chunks, t.hist.as<int>(), kb, pb);
-        GB_LAUNCH_CHECK();
-        count_launch();
+        GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * SORT_BITS));
         long long *tk = ka; ka = kb; kb = tk;
         int *tp = pa; pa = pb; pb = tp;
     }

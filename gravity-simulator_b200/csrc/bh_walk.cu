@@ -50,7 +50,8 @@ struct WalkArgs {
     const long long *K;        // sorted keys
     const int *perm;           // sorted position -> particle id
     const double4 *psorted;    // particle records in sorted order
-    int p_lo, p_hi;            // sorted positions handled by this launch
+    const int *tord;           // optional: thread q handles sorted position tord[q] (walk-key grouping), else q
+    int p_lo, p_hi;            // sorted positions (or slots of tord) handled by this launch
     double G, eps2, theta2;
     double cell2[MAX_LEVEL + 2];   // (box_length / (2 << level))^2 per child level
     double *acc;               // AoS [3n] by particle id
@@ -82,8 +83,9 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
     __shared__ double s_cell2[MAX_LEVEL + 2];
     if (threadIdx.x < MAX_LEVEL + 2) s_cell2[threadIdx.x] = a.cell2[threadIdx.x];
     __syncthreads();
-    const int p = a.p_lo + blockIdx.x * WALK_BLOCK + threadIdx.x;
-    if (p >= a.p_hi) return;
+    const int q = a.p_lo + blockIdx.x * WALK_BLOCK + threadIdx.x;
+    if (q >= a.p_hi) return;
+    const int p = a.tord ? a.tord[q] : q;
     const int idx = a.perm[p];
     const double4 me = a.psorted[p];
     const double xi = me.x, yi = me.y, zi = me.z;
@@ -177,6 +179,15 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
 }
 
 int bh_pack_walk_nodes(grav_b200_ctx *c);
+int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift);
+
+// walk key of every sorted position (reference mode: the sorted key array indexed by the ORIGINAL particle id)
+__global__ void __launch_bounds__(256) walk_keys_kernel(const long long *__restrict__ K, const int *__restrict__ perm, int n,
+                                                       long long *__restrict__ ki, int *__restrict__ pos)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) { ki[p] = K[perm[p]]; pos[p] = p; }
+}
 
 int bh_walk(grav_b200_ctx *c, double eps, double theta)
 {
@@ -199,6 +210,22 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
         a.cell2[level] = bl * bl;                              // :162 (left-hand side)
     }
     a.acc = c->acc.as<double>();
+    // Reference mode only: the walk length of a target depends on the top bits of its (unrelated) walk key, so
+    // Morton neighbours diverge.  Grouping targets by the key's level-1 octant (stable, Morton order inside a group)
+    // raises the item-count lane efficiency from 0.73 to 0.87 on a Plummer sphere (oracle statistics).
+    static const int group_bits = getenv("GRAV_B200_WALK_GROUP_BITS") ? atoi(getenv("GRAV_B200_WALK_GROUP_BITS")) : 0;
+    if (group_bits > 0 && c->bh_mode != GRAV_B200_BH_FIXED) {
+        const int n = c->n;
+        GB_TRY(t.ki.reserve(sizeof(long long) * 2 * (size_t)n));
+        GB_TRY(t.tord.reserve(sizeof(int) * 2 * (size_t)n));
+        long long *ki = t.ki.as<long long>();
+        int *pos = t.tord.as<int>();
+        walk_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a.K, a.perm, n, ki, pos + n);
+        GB_LAUNCH_CHECK();
+        count_launch();
+        GB_TRY(radix_pass(c, ki, pos + n, ki + n, pos, n, 63 - group_bits));   // digit = top group_bits bits (<= 8)
+        a.tord = pos;
+    }
     if (c->world > 1) GB_CUDA(cudaMemsetAsync(a.acc, 0, sizeof(double) * 3 * (size_t)c->n, c->stream));
     const int npos = a.p_hi - a.p_lo;
     if (npos > 0) {

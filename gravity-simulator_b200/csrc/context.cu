@@ -232,7 +232,7 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     DevTree &t = c->tree;
     DevBuf *tb[] = {&t.keys_unsorted, &t.keys, &t.perm, &t.keys_tmp, &t.perm_tmp, &t.hist, &t.bbox, &t.exp_rec,
                     &t.wsum, &t.wscan, &t.scan_tmp, &t.fc, &t.node_np, &t.node_nch, &t.node_first, &t.node_fc, &t.node_mass,
-                    &t.node_cx, &t.node_cy, &t.node_cz, &t.node_mtd, &t.node_walk, &t.posm_sorted, &t.ki, &t.counters};
+                    &t.node_cx, &t.node_cy, &t.node_cz, &t.node_mtd, &t.node_walk, &t.posm_sorted, &t.ki, &t.tord, &t.counters};
     for (DevBuf *b : tb) b->release();
     for (int i = 0; i < 2 * ST_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; i++) if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);

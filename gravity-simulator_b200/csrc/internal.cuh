@@ -84,7 +84,7 @@ struct DevTree {
     DevBuf node_mtd;                        // double[3*num_nodes] mass-weighted position sums
     DevBuf node_walk;                       // packed 64-byte walk records
     DevBuf posm_sorted;                     // double4[n]: posm in sorted (Morton) order, for the walk's leaf sums
-    DevBuf ki;                              // int64[n] per-target walk key
+    DevBuf ki, tord;                        // walk keys and target order (optional walk-key grouping)
     DevBuf counters;                        // misc device ints
 };
 

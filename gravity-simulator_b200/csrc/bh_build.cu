@@ -197,14 +197,15 @@ __global__ void __launch_bounds__(256) walk_nodes_kernel(int M, const int *__res
                                                         const double *__restrict__ mass, const double *__restrict__ cx,
                                                         const double *__restrict__ cy, const double *__restrict__ cz,
                                                         const long long *__restrict__ K, const int *__restrict__ perm,
-                                                        int fixed_mode, WalkNode *__restrict__ out)
+                                                        int fixed_mode, WalkGeo *__restrict__ geo, WalkTopo *__restrict__ topo)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= M) return;
-    WalkNode *w = out + id;      // next / level are written by rope_kernel
+    WalkGeo *g = geo + id;
+    WalkTopo *w = topo + id;     // next / level are written by rope_kernel
     const int f = first[id];
-    w->cx = cx[id]; w->cy = cy[id]; w->cz = cz[id];
-    w->kq = fixed_mode ? K[f] : K[perm[f]];
+    g->cx = cx[id]; g->cy = cy[id]; g->cz = cz[id];
+    g->kq = fixed_mode ? K[f] : K[perm[f]];
     w->fc = nchild[id] > 0 ? fc[id] : -1;
     w->first = f;
     w->mass = mass[id];
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const double4 *__res
 }
 
 // Ropes, one level at a time from the root down: the last child inherits its parent's rope.
-__global__ void __launch_bounds__(256) rope_kernel(const ExpRec *__restrict__ rec, int begin, int count, WalkNode *__restrict__ nodes)
+__global__ void __launch_bounds__(256) rope_kernel(const ExpRec *__restrict__ rec, int begin, int count, WalkTopo *__restrict__ nodes)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
@@ -365,12 +366,13 @@ int bh_pack_walk_nodes(grav_b200_ctx *c)
 {
     DevTree &t = c->tree;
     const int M = t.num_nodes;
-    GB_TRY(t.node_walk.reserve(sizeof(WalkNode) * (size_t)M));
-    WalkNode *nodes = t.node_walk.as<WalkNode>();
+    GB_TRY(t.node_walk.reserve((sizeof(WalkGeo) + sizeof(WalkTopo)) * (size_t)M));
+    WalkGeo *geo = t.node_walk.as<WalkGeo>();
+    WalkTopo *nodes = reinterpret_cast<WalkTopo *>(geo + M);   // second plane
     walk_nodes_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(M, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
                                                             t.node_fc.as<int>(), t.node_mass.as<double>(), t.node_cx.as<double>(),
                                                             t.node_cy.as<double>(), t.node_cz.as<double>(), t.keys.as<long long>(),
-                                                            t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0, nodes);
+                                                            t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0, geo, nodes);
     GB_LAUNCH_CHECK();
     count_launch();
     GB_TRY(t.posm_sorted.reserve(sizeof(double4) * (size_t)t.n));

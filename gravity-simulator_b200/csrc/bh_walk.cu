@@ -46,7 +46,8 @@ constexpr int WALK_BLOCK = 128;
 #endif
 
 struct WalkArgs {
-    const WalkNode *nodes;
+    const WalkGeo *geo;        // plane 0: com + key
+    const WalkTopo *topo;      // plane 1: topology + mass
     const long long *K;        // sorted keys
     const int *perm;           // sorted position -> particle id
     const double4 *psorted;    // particle records in sorted order
@@ -59,14 +60,24 @@ struct WalkArgs {
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-struct NodeRec {   // the 48 bytes of a WalkNode every visit needs, as loaded (three 16-byte read-only loads)
-    int4 A, B, C;
-};
-__device__ __forceinline__ NodeRec load_rec(const WalkNode *nodes, int node)
+// 256-bit read-only global load (sm_100: LDG.E.ENL2.256).  The walk is bound by L1 data-pipe wavefronts
+// (l1tex__data_pipe_lsu_wavefronts 78 % of peak, profiles/r1_walk_state_machine_n256k.txt): every load instruction
+// of a warp costs one wavefront per distinct 128-byte line its lanes touch, so a node visit is served by TWO load
+// instructions (32 + 16 bytes) instead of three, and a particle record by ONE instead of two.
+__device__ __forceinline__ void ldg256(const void *p, long long &a, long long &b, long long &c, long long &d)
 {
-    const int4 *q = reinterpret_cast<const int4 *>(nodes + node);
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+struct NodeRec {   // a whole WalkNode as two 256-bit loads (the mass rides along: no third load on accept)
+    long long cx, cy, cz, kq;   // raw bits
+    long long fc_next, first_lc, mass, pad;
+};
+__device__ __forceinline__ NodeRec load_rec(const WalkGeo *geo, const WalkTopo *topo, int node)
+{
     NodeRec r;
-    r.A = __ldg(q); r.B = __ldg(q + 1); r.C = __ldg(q + 2);
+    ldg256(geo + node, r.cx, r.cy, r.cz, r.kq);
+    ldg256(topo + node, r.fc_next, r.first_lc, r.mass, r.pad);
     return r;
 }
 
@@ -92,26 +103,26 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
     const long long ki = FIXED ? a.K[p] : a.K[idx];
     double ax = 0.0, ay = 0.0, az = 0.0;
 
-    int node = __ldg(&a.nodes[0].fc);   // the root is always expanded
+    int node = __ldg(&a.topo[0].fc);   // the root is always expanded
 #if WALK_VARIANT == 0
-    NodeRec rec = load_rec(a.nodes, node);
+    NodeRec rec = load_rec(a.geo, a.topo, node);
 #endif
     int leaf_pos = 0, leaf_rem = 0, leaf_next = -1;
     while (node >= 0) {
 #if WALK_VARIANT == 1
-        const NodeRec rec = load_rec(a.nodes, node);
+        const NodeRec rec = load_rec(a.geo, a.topo, node);
 #endif
         bool have = false;              // this trip produced a source
         bool from_node = false;         // ... which is the current node (else: particle at sorted position src_pos)
         int src_pos = 0;
-        double sx = 0.0, sy = 0.0, sz = 0.0;
+        double sx = 0.0, sy = 0.0, sz = 0.0, msrc_node = 0.0;
         int new_node = node;
         if (leaf_rem == 0) {
-            const double cx = __hiloint2double(rec.A.y, rec.A.x), cy = __hiloint2double(rec.A.w, rec.A.z);
-            const double cz = __hiloint2double(rec.B.y, rec.B.x);
-            const long long kq = ((long long)rec.B.w << 32) | (unsigned)rec.B.z;
-            const int fc = rec.C.x, next = rec.C.y, first = rec.C.z;
-            const int level = rec.C.w >> WALK_COUNT_BITS, count = rec.C.w & ((1 << WALK_COUNT_BITS) - 1);
+            const double cx = __longlong_as_double(rec.cx), cy = __longlong_as_double(rec.cy), cz = __longlong_as_double(rec.cz);
+            const long long kq = rec.kq;
+            const int fc = (int)rec.fc_next, next = (int)(rec.fc_next >> 32), first = (int)rec.first_lc;
+            const int lc = (int)(rec.first_lc >> 32);
+            const int level = lc >> WALK_COUNT_BITS, count = lc & ((1 << WALK_COUNT_BITS) - 1);
             const int shift = 3 * (MAX_LEVEL - level);
             const bool leaf = fc < 0;
             const bool inside = ((ki ^ kq) >> shift) == 0;
@@ -123,7 +134,7 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
             }
             if (accepted) {
                 have = true; from_node = true;
-                sx = cx; sy = cy; sz = cz;
+                sx = cx; sy = cy; sz = cz; msrc_node = __longlong_as_double(rec.mass);
                 new_node = next;
             } else if (leaf) {
                 leaf_pos = first;
@@ -144,16 +155,18 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
         double msrc = 0.0;
         if (have) {
             if (from_node) {
-                msrc = __ldg(&a.nodes[node].mass);
+                msrc = msrc_node;
             } else {
-                const double4 q = a.psorted[src_pos];
-                sx = q.x; sy = q.y; sz = q.z; msrc = q.w;
+                long long qx, qy, qz, qw;
+                ldg256(a.psorted + src_pos, qx, qy, qz, qw);
+                sx = __longlong_as_double(qx); sy = __longlong_as_double(qy); sz = __longlong_as_double(qz);
+                msrc = __longlong_as_double(qw);
             }
         }
 #if WALK_VARIANT == 0
-        if (new_node != node && new_node >= 0) rec = load_rec(a.nodes, new_node);
+        if (new_node != node && new_node >= 0) rec = load_rec(a.geo, a.topo, new_node);
 #else
-        if (new_node != node && new_node >= 0) prefetch_l1(a.nodes + new_node);
+        if (new_node != node && new_node >= 0) prefetch_l1(a.geo + new_node);
 #endif
         node = new_node;
         if (have) {
@@ -194,7 +207,8 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
     DevTree &t = c->tree;
     GB_TRY(bh_pack_walk_nodes(c));
     WalkArgs a{};
-    a.nodes = t.node_walk.as<WalkNode>();
+    a.geo = t.node_walk.as<WalkGeo>();
+    a.topo = reinterpret_cast<const WalkTopo *>(a.geo + t.num_nodes);
     a.K = t.keys.as<long long>();
     a.perm = t.perm.as<int>();
     a.psorted = t.posm_sorted.as<double4>();

@@ -51,9 +51,14 @@ enum { ST_TOTAL = 0, ST_GATHER = 1, ST_FORCE = 2, ST_MORTON = 3, ST_SORT = 4, ST
 // the mass only when the node is accepted.
 // `next` is the "rope": the node that follows in depth-first order when this node's subtree is skipped
 // (next sibling, else the parent's rope; -1 ends the walk), which makes the walk stackless.
-struct WalkNode {
+// Stored as two planes of 32-byte records (geo[M] then topo[M] in one buffer) rather than one 64-byte record: the
+// walk is bound by L1 wavefronts = distinct 128-byte lines per load instruction, and lanes that are a few siblings
+// apart then share lines (4 records per line instead of 2).
+struct WalkGeo {
     double cx, cy, cz;
     long long kq;      // key the inclusion test compares against (mode dependent)
+};
+struct WalkTopo {
     int fc;            // id of the first child, -1 for a leaf
     int next;
     int first;         // sorted position of the node's first particle
@@ -62,7 +67,7 @@ struct WalkNode {
     long long pad;
 };
 constexpr int WALK_COUNT_BITS = 26;
-static_assert(sizeof(WalkNode) == 64, "WalkNode layout");
+static_assert(sizeof(WalkGeo) == 32 && sizeof(WalkTopo) == 32, "walk record layout");
 
 // Device-side linear octree (layout in DESIGN.md "BH data layout")
 struct DevTree {

@@ -252,6 +252,10 @@ int grav_b200_ctx_set_system(grav_b200_ctx *c, int n, const double *x, const dou
     if (!c) { set_error("NULL context"); return GRAV_B200_EINVAL; }
     if (!x || !m) { set_error("NULL array pointer"); return GRAV_B200_EINVAL; }
     if (n < 1) { set_error("num_particles must be >= 1, got %d", n); return GRAV_B200_EINVAL; }
+    if (n > GRAV_B200_MAX_PARTICLES) {   // 32-bit work-unit and packed level/count fields; 2^24 is BASELINE.json's largest size
+        set_error("num_particles %d exceeds the supported maximum %d", n, GRAV_B200_MAX_PARTICLES);
+        return GRAV_B200_EINVAL;
+    }
     GB_CUDA(cudaSetDevice(c->device));
     c->n = n;
     c->n_pad = ((n + SRC_PAD - 1) / SRC_PAD) * SRC_PAD;

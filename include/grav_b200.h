@@ -43,6 +43,10 @@ extern "C" {
 #define GRAV_B200_METHOD_MASSLESS   2
 #define GRAV_B200_METHOD_BARNES_HUT 3
 
+/* Largest supported particle count (2^24, the largest size in BASELINE.json): work-unit indices are 32-bit and
+ * the walk records pack the particle count in 26 bits.  Larger systems are rejected with GRAV_B200_EINVAL. */
+#define GRAV_B200_MAX_PARTICLES (1 << 24)
+
 /* Barnes-Hut walk semantics (see DESIGN.md "BH modes") */
 #define GRAV_B200_BH_REFERENCE 0  /* bug-for-bug with src/acceleration_barnes_hut.c:78-248 (default) */
 #define GRAV_B200_BH_FIXED     1  /* opt-in: correct inclusion test, leaves never dropped            */

@@ -221,13 +221,21 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const double4 *__res
     if (p < n) out[p] = posm[perm[p]];
 }
 
-// Ropes, one level at a time from the root down: the last child inherits its parent's rope.
-__global__ void __launch_bounds__(256) rope_kernel(const ExpRec *__restrict__ rec, int begin, int count, WalkTopo *__restrict__ nodes)
+// Ropes in one launch: child k < nch-1 is followed by its next sibling (id + 1); the last child inherits its parent's
+// rope, found by climbing while the node is itself a last child (1.3 steps on average); the root's rope ends the walk.
+__global__ void __launch_bounds__(256) rope_kernel(const ExpRec *__restrict__ rec, int ne, WalkTopo *__restrict__ nodes)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const ExpRec r = rec[begin + t];
-    const int my_next = (r.id == 0) ? -1 : nodes[r.id].next;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= ne) return;
+    const ExpRec r = rec[u];
+    int my_next = -1;
+    int v = u;
+    while (true) {
+        const int parent = rec[v].parent;
+        if (parent < 0) break;                                   // reached the root: -1
+        if (rec[v].rank < rec[parent].nch - 1) { my_next = rec[v].id + 1; break; }
+        v = parent;
+    }
     for (int k = 0; k < r.nch; k++) {
         const int cid = r.first_child + k;
         nodes[cid].next = (k < r.nch - 1) ? cid + 1 : my_next;
@@ -379,13 +387,9 @@ int bh_pack_walk_nodes(grav_b200_ctx *c)
     gather_sorted_kernel<<<(t.n + 255) / 256, 256, 0, c->stream>>>(c->posm.as<double4>(), t.perm.as<int>(), t.n, t.posm_sorted.as<double4>());
     GB_LAUNCH_CHECK();
     count_launch();
-    for (int l = 0; l < t.max_level; l++) {
-        const int begin = t.level_off[l], count = t.level_off[l + 1] - begin;
-        if (count <= 0) continue;
-        rope_kernel<<<(count + 255) / 256, 256, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, nodes);
-        GB_LAUNCH_CHECK();
-        count_launch();
-    }
+    rope_kernel<<<(t.num_expanded + 255) / 256, 256, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), t.num_expanded, nodes);
+    GB_LAUNCH_CHECK();
+    count_launch();
     return GRAV_B200_OK;
 }
 

@@ -1,0 +1,61 @@
+"""GPU parity fuzz: seeded random systems with awkward geometry (planar, collinear, duplicates, huge dynamic range,
+zero masses, tiny N) through every method, against the CPU oracle.  Barnes-Hut outputs must be bit-identical."""
+import numpy as np
+import pytest
+
+from conftest import max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([1, 2, 3, 5, 8, 17, 33, 100, 257, 600, 1500, 4000]))
+    kind = seed % 7
+    x = rng.normal(size=(n, 3))
+    if kind == 1:
+        x[:, 2] = 0.0                                   # planar
+    elif kind == 2:
+        x[:, 1:] = 0.0                                  # collinear
+    elif kind == 3 and n > 3:
+        x[n // 2:] = x[: n - n // 2] + (rng.random((n - n // 2, 3)) < 0.5) * 1e-12      # near-duplicates and exact duplicates
+    elif kind == 4:
+        x *= 10.0 ** rng.uniform(-6, 6, size=(n, 1))    # huge dynamic range
+    elif kind == 5:
+        x = rng.random((n, 3)) * np.array([1.0, 1e-3, 1e3]) + 1e6     # far from the origin, anisotropic
+    elif kind == 6:
+        x = np.round(x * 4) / 4                         # lattice: many exact coincidences and ties
+    m = rng.random(n) + 0.01
+    if seed % 3 == 0 and n > 2:
+        m[rng.random(n) < 0.4] = 0.0                    # massless particles sprinkled in
+    G = float(10.0 ** rng.uniform(-3, 1))
+    eps = 0.0 if seed % 2 else float(10.0 ** rng.uniform(-4, -1))
+    theta = float(rng.choice([0.0, 0.2, 0.5, 0.8, 1.0, 1.7]))
+    leaf = int(rng.choice([1, 1, 2, 3, 8, 40]))
+    return x, m, G, eps, theta, leaf
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_fuzz_all_methods(gb, oracle, seed):
+    x, m, G, eps, theta, leaf = make_case(seed)
+    # Barnes-Hut: tree and accelerations bit-identical (NaN where the reference gives NaN)
+    t, to = gb.construct_octree(x, m, leaf), oracle.construct_octree(x, m, leaf)
+    assert t["num_nodes"] == to["num_nodes"] and (t["box_width"] == to["box_width"] or np.isnan(to["box_width"]))
+    for k in ("keys", "sorted_indices", "num_particles", "num_children", "first_particle", "first_child", "mass", "com_x", "com_y", "com_z"):
+        assert np.array_equal(t[k], to[k], equal_nan=True), (seed, k)
+    a = gb.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
+    ao = oracle.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
+    assert np.array_equal(a, ao, equal_nan=True), (seed, "bh", max_rel_err(np.nan_to_num(a), np.nan_to_num(ao)))
+    # direct sums: 1e-12 on every particle where the reference is finite and non-zero; NaN/inf pattern identical
+    for method in ("pairwise", "massless"):
+        a = gb.acceleration(x, m, G, method, eps)
+        ao = oracle.acceleration(x, m, G, method, eps)
+        fin = np.isfinite(ao).all(axis=1)
+        assert np.array_equal(np.isfinite(a).all(axis=1), fin), (seed, method, "finite pattern")
+        if fin.any():
+            scale = np.abs(ao[fin]).max()
+            num = np.linalg.norm(a[fin] - ao[fin], axis=1)
+            den = np.maximum(np.linalg.norm(ao[fin], axis=1), 1e-30)
+            # relative to the particle's own acceleration, or (when that is the result of massive cancellation) 1e-14 of
+            # the largest term sum in the system
+            assert np.all((num / den <= 1e-12) | (num <= 1e-14 * scale)), (seed, method, float(np.max(num / den)))

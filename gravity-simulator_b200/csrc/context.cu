@@ -236,6 +236,7 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     for (DevBuf *b : tb) b->release();
     for (int i = 0; i < 2 * ST_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; i++) if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
+    if (c->small_pinned) cudaFreeHost(c->small_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -444,6 +445,12 @@ static int one_shot(double *a, int n, const double *x, const double *m, double G
 
 int grav_b200_acceleration_pairwise(double *a, int n, const double *x, const double *m, double G, double eps)
 {
+    if (n >= 1 && n <= 256 && a && x && m && eps >= 0.0) {   // small systems: one launch, zero-copy (direct_sum.cu)
+        std::lock_guard<std::mutex> lk(g_mu);
+        grav_b200_ctx *c;
+        GB_TRY(default_ctx(&c));
+        return direct_sum_small_host(c, a, n, x, m, G, eps);
+    }
     return one_shot(a, n, x, m, G, GRAV_B200_METHOD_PAIRWISE, eps, 0.0, 1);
 }
 int grav_b200_acceleration_massless(double *a, int n, const double *x, const double *m, double G, double eps)

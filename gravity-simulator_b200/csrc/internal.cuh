@@ -125,6 +125,7 @@ struct grav_b200_ctx {
     int bh_mode = 0;
     cudaEvent_t user_ev[8] = {};
     gb::DevBuf l2_flush;
+    double *small_pinned = nullptr;   // mapped pinned host staging of the small-N one-shot path (in: 4n doubles, out: 3n)
     cudaEvent_t ev[2 * gb::ST_COUNT] = {};
     bool ev_valid[gb::ST_COUNT] = {};
 };
@@ -133,6 +134,7 @@ namespace gb {
 // direct_sum.cu
 int direct_sum_pairwise(grav_b200_ctx *c, double eps);
 int direct_sum_massless(grav_b200_ctx *c, double eps);
+int direct_sum_small_host(grav_b200_ctx *c, double *a, int n, const double *x, const double *m, double G, double eps);
 // pack.cu
 int pack_posm(grav_b200_ctx *c, const double *d_x_aos, const double *d_m);   // device AoS -> posm
 int pack_positions(grav_b200_ctx *c, const double *d_x_aos);

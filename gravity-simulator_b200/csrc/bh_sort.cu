@@ -126,6 +126,21 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;        // 4096 pairs per C
 constexpr int SORT_WCHUNK = 32 * SORT_ROUNDS;                // 512 pairs per warp
 constexpr size_t SORT_SMEM = (size_t)SORT_TILE * (sizeof(long long) + sizeof(int));   // staging: 48 KiB
 
+__device__ __forceinline__ unsigned match_digit(int d, bool valid)
+{
+#ifdef SORT_BALLOT_MATCH
+    unsigned same = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < SORT_BITS; b++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1);
+        same &= ((d >> b) & 1) ? bal : ~bal;
+    }
+    return same;
+#else
+    (void)valid;
+    return __match_any_sync(0xffffffffu, d);
+#endif
+}
 __device__ __forceinline__ int digit_of(long long k, int shift) { return (int)((unsigned long long)k >> shift) & (SORT_RADIX - 1); }
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const long long *__restrict__ keys, int n, int shift,
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const long long
         const int p = base + r * SORT_THREADS + threadIdx.x;      // order is irrelevant for counting: coalesced
         const bool valid = p < n;
         const int d = valid ? digit_of(keys[p], shift) : SORT_RADIX;
-        const unsigned same = __match_any_sync(0xffffffffu, d);
+        const unsigned same = match_digit(d, valid);
         if (valid && (same >> lane) == 1u) atomicAdd(&cnt[d], __popc(same));   // one atomic per distinct digit per warp
     }
     __syncthreads();
@@ -179,7 +194,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const long l
         k[r] = valid ? keys_in[base + li] : 0;
         v[r] = valid ? vals_in[base + li] : 0;
         const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
-        const unsigned same = __match_any_sync(0xffffffffu, d);
+        const unsigned same = match_digit(d, valid);
         if (valid && (same >> lane) == 1u) wcnt[warp][d] += __popc(same);
         __syncwarp();
     }
@@ -220,7 +235,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const long l
         const int li = wbase + r * 32 + lane;
         const bool valid = li < tile_n;
         const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
-        const unsigned same = __match_any_sync(0xffffffffu, d);
+        const unsigned same = match_digit(d, valid);
         if (valid) {
             const int slot = wcnt[warp][d] + __popc(same & lt);
             skeys[slot] = k[r];

@@ -1,0 +1,30 @@
+"""Small end-to-end run of every kernel family, meant to be executed under compute-sanitizer."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from conftest import load_package
+gb = load_package()
+import numpy as np
+from gravity_simulator_b200 import ics
+from oracle.bind import jacobi_inputs
+for n in (9, 300, 1111, 5000):
+    x, v, m, G = ics.clustered(n, n) if n != 9 else ics.solar_system()
+    for method, kw in (("pairwise", {}), ("massless", {}), ("barnes_hut", dict(opening_angle=0.5, max_num_particles_per_leaf=1)),
+                       ("barnes_hut", dict(opening_angle=0.7, max_num_particles_per_leaf=5))):
+        a = gb.acceleration(x, m, G, method, 0.01, **kw)
+        assert np.isfinite(a).all()
+    gb.construct_octree(x, m, 2)
+    mm = m.copy(); mm[n // 3:] = 0.0
+    jx, eta = jacobi_inputs(x, mm)
+    gb.whfast_acceleration(x, mm, G, jx, eta, "massless", 0.0)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.leapfrog_begin(1e-3, "barnes_hut", 0.01, 0.5, 1)
+        c.leapfrog_steps(1e-3, 2)
+        c.energy(); c.positions(); c.velocities()
+        c.leapfrog_end()
+x, v, m, G = ics.plummer(40000, 1)
+gb.acceleration(x, m, G, "pairwise", 0.01)      # fast kernel + fix-up + special-tile kernel
+gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)
+print("sanitize_smoke done")

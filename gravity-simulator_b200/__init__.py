@@ -104,6 +104,7 @@ ABI_SYMBOLS = [
     "grav_b200_kernel_launch_count", "grav_b200_measure_fp64_peak", "grav_b200_ctx_event_record",
     "grav_b200_ctx_event_elapsed_ms", "grav_b200_ctx_flush_l2", "grav_b200_ctx_mark_positions_sharded",
     "grav_b200_host_register", "grav_b200_host_unregister",
+    "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
 ]
 SHIM_SYMBOLS = [
     "get_new_acceleration_param", "finalize_acceleration_param", "acceleration", "acceleration_barnes_hut",
@@ -147,6 +148,10 @@ def load():
     abi.grav_b200_ctx_leapfrog_end.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_leapfrog_steps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
     abi.grav_b200_ctx_energy.argtypes = [C.c_void_p, c_double_p]
+    abi.grav_b200_ctx_whfast_begin.argtypes = [C.c_void_p, c_int_p, C.c_int, C.c_double, C.c_double, C.c_int]
+    abi.grav_b200_ctx_whfast_steps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
+    abi.grav_b200_ctx_whfast_get_state.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p]
+    abi.grav_b200_ctx_whfast_end.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_synchronize.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_last_timing_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
     abi.grav_b200_measure_fp64_peak.argtypes = [C.c_int, c_double_p, c_double_p]
@@ -386,6 +391,33 @@ class Context:
 
     def leapfrog_steps(self, dt, num_steps):
         check_rc(self.abi.grav_b200_ctx_leapfrog_steps(self.h, float(dt), int(num_steps)))
+
+    # device-resident WHFast (src/integrator_whfast.c:200-407)
+    def whfast_begin(self, dt, method="massless", softening_length=0.0, remove_invalid_particles=True, ids=None):
+        meth = METHODS[method] if isinstance(method, str) else int(method)
+        pid = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int32)
+            pid = ids.ctypes.data_as(c_int_p)
+        check_rc(self.abi.grav_b200_ctx_whfast_begin(self.h, pid, meth, float(softening_length), float(dt),
+                                                     int(bool(remove_invalid_particles))))
+
+    def whfast_steps(self, dt, num_steps):
+        check_rc(self.abi.grav_b200_ctx_whfast_steps(self.h, float(dt), int(num_steps)))
+        self.n = int(self.abi.grav_b200_ctx_num_particles(self.h))
+
+    def whfast_state(self, snapshot=False):
+        """dict(x, v, m, ids) in the current particle order; snapshot=True applies the reference's output convention."""
+        n = int(self.abi.grav_b200_ctx_num_particles(self.h))
+        x = np.empty((n, 3)); v = np.empty((n, 3)); m = np.empty(n); ids = np.empty(n, dtype=np.int32)
+        nn = C.c_int()
+        check_rc(self.abi.grav_b200_ctx_whfast_get_state(self.h, int(bool(snapshot)), C.byref(nn), ids.ctypes.data_as(c_int_p),
+                                                         _dp(x), _dp(v), _dp(m)))
+        assert nn.value == n
+        return {"x": x, "v": v, "m": m, "ids": ids}
+
+    def whfast_end(self):
+        check_rc(self.abi.grav_b200_ctx_whfast_end(self.h))
 
     def energy(self) -> float:
         e = C.c_double()

@@ -225,6 +225,7 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    whfast_state_free(c);
     comm_destroy(c);
     DevBuf *bufs[] = {&c->posm, &c->vel, &c->acc, &c->xcomp, &c->vcomp, &c->stage_a, &c->stage_b, &c->stage_c, &c->stage_d,
                       &c->partials, &c->misc, &c->msrc, &c->msrc_id, &c->msrc_altm, &c->l2_flush, &c->mflag, &c->mrank};

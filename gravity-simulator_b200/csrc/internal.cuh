@@ -122,6 +122,8 @@ struct grav_b200_ctx {
     double lf_eps = 0.0, lf_theta = 1.0, lf_dt = 0.0;
     bool lf_ready = false;
 
+    void *wh = nullptr;   // gb::WhfastState (whfast_resident.cu)
+
     int bh_mode = 0;
     cudaEvent_t user_ev[8] = {};
     gb::DevBuf l2_flush;
@@ -144,6 +146,8 @@ int whfast_accel(grav_b200_ctx *c, const double *d_jacobi_x, const double *d_eta
 // bh_*.cu
 int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double box_width);
 int bh_walk(grav_b200_ctx *c, double eps, double theta);
+// whfast_resident.cu
+void whfast_state_free(grav_b200_ctx *c);
 // comm.cu
 int comm_init(grav_b200_ctx *c, const void *uid);
 void comm_destroy(grav_b200_ctx *c);

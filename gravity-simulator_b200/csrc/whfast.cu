@@ -134,6 +134,18 @@ __global__ void __launch_bounds__(128) whfast_kernel(int n, const double4 *__res
 
 int massive_list(grav_b200_ctx *c, int *n_massive);   // direct_sum.cu: fills c->msrc_id (ids) and c->stage_d2 ranks
 
+// resident WHFast (whfast_resident.cu): the caller already holds the massive list of the current particle order
+int whfast_accel_with_list(grav_b200_ctx *c, const double *d_jx, const double *d_eta, double eps, const int *list, int nl,
+                           const int *rank)
+{
+    const int n = c->n;
+    whfast_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->posm.as<double4>(), c->G, d_jx, d_eta, eps * eps * eps, list, nl, rank,
+                                                         c->acc.as<double>());
+    GB_LAUNCH_CHECK();
+    count_launch();
+    return GRAV_B200_OK;
+}
+
 int whfast_accel(grav_b200_ctx *c, const double *d_jx, const double *d_eta, double eps, bool massless)
 {
     const int n = c->n;

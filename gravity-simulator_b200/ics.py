@@ -82,3 +82,24 @@ def solar_system():
     from pathlib import Path
     z = np.load(Path(__file__).resolve().parent.parent / "tests" / "golden" / "solar_system.npz")
     return z["x"].copy(), z["v"].copy(), z["m"].copy(), float(z["G"])
+
+
+def asteroid_belt(k: int = 100000, seed: int = 3, ecc: float = 0.12, inc: float = 0.05, grazers: int = 0):
+    """Config 3: the built-in solar system plus k massless asteroids on near-Keplerian orbits with semi-major axes in
+    [2, 3.35) AU (the range of examples/kirkwood_gaps/c/kirkwood_gaps.c:49-79), speeds perturbed by up to +-ecc.
+    `grazers` of them are turned into Sun-grazing / hyperbolic bodies whose Kepler solve fails with dt = 180 d, which
+    exercises WHFast's removal of invalid particles (src/integrator_whfast.c:551)."""
+    xs, vs, ms, G = solar_system()
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(2.0, 3.35, k)
+    ph = rng.uniform(0.0, 2.0 * np.pi, k)
+    pos = np.stack([a * np.cos(ph), a * np.sin(ph), rng.normal(0.0, inc, k)], axis=1)
+    vc = np.sqrt(G * ms[0] / a) * (1.0 + rng.uniform(-ecc, ecc, k))
+    vel = np.stack([-vc * np.sin(ph), vc * np.cos(ph), rng.normal(0.0, 1e-4, k)], axis=1)
+    if grazers:
+        pos[:grazers] *= rng.uniform(0.002, 0.02, (grazers, 1))
+        vel[:grazers] *= rng.uniform(0.0, 30.0, (grazers, 1))
+    x = np.concatenate([xs, pos + xs[0]])
+    v = np.concatenate([vs, vel + vs[0]])
+    m = np.concatenate([ms, np.zeros(k)])
+    return np.ascontiguousarray(x), np.ascontiguousarray(v), m, G

@@ -153,6 +153,27 @@ int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *ctx, int method, double softenin
 int grav_b200_ctx_leapfrog_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
 int grav_b200_ctx_leapfrog_end(grav_b200_ctx *ctx);
 
+/* Device-resident WHFast on the resident state (one GPU); mirrors whfast(), src/integrator_whfast.c:200-407, with
+ * the particle order, eta, the Kepler drift, both coordinate transforms and the kick on the device -- bit-identical
+ * to the reference after any number of steps.
+ *   whfast_begin(): particle_ids[n] host array or NULL (= 0..n-1); sorts by distance from id 0 (:242), eta and
+ *                   cartesian_to_jacobi (:266-267), the first interaction acceleration and the half kick (:268-273).
+ *                   method: pairwise or massless (:817-837).  remove_invalid_particles as IntegratorParam's flag.
+ *   whfast_steps(): num_steps times { sort by Jacobi distance (:301-311), eta (:312), Kepler drift with the optional
+ *                   removal of unsolvable particles (:315-327), jacobi_to_cartesian (:330), acceleration (:333),
+ *                   kick (:340) }.  The particle count can shrink (ctx_num_particles()).
+ *   whfast_get_state(): downloads n, ids, x, v, m (any may be NULL) in the current particle order.  snapshot != 0
+ *                   first brings the velocities back by half a step, as the reference does before an output
+ *                   (:346-351) -- and like the reference leaves x/v in that state; snapshot == 0 returns what the
+ *                   last step left (v from the half-step Jacobi velocities), the reference's state at loop exit.
+ *   whfast_end():   releases the integrator state. */
+int grav_b200_ctx_whfast_begin(grav_b200_ctx *ctx, const int *particle_ids, int method, double softening_length,
+                               double dt, int remove_invalid_particles);
+int grav_b200_ctx_whfast_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
+int grav_b200_ctx_whfast_get_state(grav_b200_ctx *ctx, int snapshot, int *n_out, int *particle_ids, double *x,
+                                   double *v, double *m);
+int grav_b200_ctx_whfast_end(grav_b200_ctx *ctx);
+
 /* Total energy of the resident state, same definition as compute_energy, src/utils.c:27-59
  * (unsoftened potential).  Collective when world_size>1. */
 int grav_b200_ctx_energy(grav_b200_ctx *ctx, double *energy);

@@ -76,6 +76,18 @@ class Oracle:
         L.oracle_barnes_hut.argtypes = [dp, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
         L.oracle_energy.argtypes = [C.c_int, dp, dp, dp, C.c_double]
         L.oracle_energy.restype = C.c_double
+        L.oracle_sort_by_distance.argtypes = [C.c_int, ip, dp, dp, dp, C.c_int]
+        L.oracle_whfast_eta.argtypes = [dp, C.c_int, dp]
+        L.oracle_whfast_eta.restype = None
+        L.oracle_cartesian_to_jacobi.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp]
+        L.oracle_cartesian_to_jacobi.restype = None
+        L.oracle_jacobi_to_cartesian.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp]
+        L.oracle_jacobi_to_cartesian.restype = None
+        L.oracle_stumpff.argtypes = [dp, C.c_double]
+        L.oracle_stumpff.restype = None
+        L.oracle_whfast_drift.argtypes = [C.c_int, dp, dp, ip, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int]
+        L.oracle_whfast_integrate.argtypes = [C.c_int, ip, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                              C.c_double, C.c_int, C.c_int64, C.c_int, dp]
 
     def acceleration(self, x, m, G, method="pairwise", softening_length=0.0, opening_angle=1.0,
                      max_num_particles_per_leaf=1, fixed=False):
@@ -98,6 +110,45 @@ class Oracle:
         fn = self.L.oracle_whfast_pairwise if method == "pairwise" else self.L.oracle_whfast_massless
         fn(_d(a), m.shape[0], _d(x), _d(m), G, _d(jx), _d(eta), softening_length)
         return a
+
+    def whfast_integrate(self, x, v, m, G, dt, tf, method="massless", softening_length=0.0, remove_invalid=True,
+                         max_steps=-1, ids=None, snapshot=False):
+        """whfast() with output disabled (src/integrator_whfast.c:200-407): returns dict(x, v, m, ids, a) as the
+        reference leaves them (v at the half step, particles in the last distance-sorted order)."""
+        x = _f64(x, (-1, 3)).copy(); v = _f64(v, (-1, 3)).copy(); m = _f64(m, (-1,)).copy(); n = m.shape[0]
+        ids = np.arange(n, dtype=np.int32) if ids is None else np.ascontiguousarray(ids, dtype=np.int32).copy()
+        a = np.zeros_like(x)
+        n2 = self.L.oracle_whfast_integrate(n, ids.ctypes.data_as(ip), _d(x), _d(v), _d(m), G, dt, tf, METHODS[method],
+                                            softening_length, int(remove_invalid), max_steps, int(snapshot), _d(a))
+        if n2 < 0:
+            raise RuntimeError(f"oracle_whfast_integrate -> {n2}")
+        return {"x": x[:n2], "v": v[:n2], "m": m[:n2], "ids": ids[:n2], "a": a[:n2]}
+
+    def whfast_stages(self, x, v, m, G, dt):
+        """Same sequence as Reference.whfast_stages with the restated functions."""
+        x = _f64(x, (-1, 3)).copy(); v = _f64(v, (-1, 3)).copy(); m = _f64(m, (-1,)).copy(); n = m.shape[0]
+        eta, jx, jv = self.jacobi_state(x, v, m)
+        out = {"eta": eta.copy(), "jx0": jx.copy(), "jv0": jv.copy()}
+        ids = np.arange(n, dtype=np.int32)
+        assert self.L.oracle_whfast_drift(n, _d(jx), _d(jv), ids.ctypes.data_as(ip), _d(x), _d(v), _d(m), _d(eta), G, dt, 0) == n
+        out["jx1"], out["jv1"] = jx.copy(), jv.copy()
+        x2 = np.empty_like(x); v2 = np.empty_like(v)
+        self.L.oracle_jacobi_to_cartesian(_d(x2), _d(v2), n, _d(jx), _d(jv), _d(m), _d(eta))
+        out["x1"], out["v1"] = x2, v2
+        return out
+
+    def stumpff(self, z):
+        c = np.empty(4)
+        self.L.oracle_stumpff(_d(c), float(z))
+        return c
+
+    def jacobi_state(self, x, v, m):
+        """eta, jacobi_x, jacobi_v (src/integrator_whfast.c:1266-1279, :682-724)."""
+        x = _f64(x, (-1, 3)); v = _f64(v, (-1, 3)); m = _f64(m, (-1,)); n = m.shape[0]
+        eta = np.empty(n); jx = np.zeros_like(x); jv = np.zeros_like(v)
+        self.L.oracle_whfast_eta(_d(eta), n, _d(m))
+        self.L.oracle_cartesian_to_jacobi(_d(jx), _d(jv), n, _d(x), _d(v), _d(m), _d(eta))
+        return eta, jx, jv
 
     def morton_keys(self, x):
         x = _f64(x, (-1, 3)); n = x.shape[0]
@@ -228,6 +279,58 @@ class Reference:
             raise RuntimeError(f"reference whfast_acceleration -> {rc}")
         return a
 
+    def _probe(self):
+        if not hasattr(self, "P"):
+            self.P = C.CDLL(str(PROBE_SO))
+            self.P.probe_whfast_acceleration.argtypes = [dp, C.c_int, dp, dp, C.c_double, dp, dp, C.c_int, C.c_double]
+        P = self.P
+        if not hasattr(P, "_whfast_ready"):
+            P.probe_whfast_run.argtypes = [C.c_int, ip, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                                           C.c_int, C.c_int]
+            P.probe_whfast_c2j.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp]
+            P.probe_whfast_c2j.restype = None
+            P.probe_whfast_j2c.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp]
+            P.probe_whfast_j2c.restype = None
+            P.probe_stumpff.argtypes = [dp, C.c_double]
+            P.probe_stumpff.restype = None
+            P.probe_whfast_drift.argtypes = [C.c_int, ip, dp, dp, dp, C.c_double, dp, dp, dp, C.c_double, C.c_int]
+            P._whfast_ready = True
+        return P
+
+    def whfast_run(self, x, v, m, G, dt, tf, method="massless", softening_length=0.0, remove_invalid=True, ids=None):
+        """The reference's whfast() (src/integrator_whfast.c:200-407), output disabled, through ref_whfast_probe.c.
+        Run with OMP_NUM_THREADS=1 when particles can be removed: the OpenMP build fills remove_idx_list racily (:553-562)."""
+        P = self._probe()
+        x = _f64(x, (-1, 3)).copy(); v = _f64(v, (-1, 3)).copy(); m = _f64(m, (-1,)).copy(); n = m.shape[0]
+        ids = np.arange(n, dtype=np.int32) if ids is None else np.ascontiguousarray(ids, dtype=np.int32).copy()
+        n2 = P.probe_whfast_run(n, ids.ctypes.data_as(ip), _d(x), _d(v), _d(m), G, dt, tf, METHODS[method], softening_length,
+                                int(remove_invalid), 0)
+        if n2 < 0:
+            raise RuntimeError(f"reference whfast() -> {n2}")
+        return {"x": x[:n2], "v": v[:n2], "m": m[:n2], "ids": ids[:n2]}
+
+    def whfast_stages(self, x, v, m, G, dt):
+        """eta, cartesian_to_jacobi, whfast_drift (no removal) and jacobi_to_cartesian of the reference, one after the
+        other on the given (already distance-sorted) system; returns every intermediate."""
+        P = self._probe()
+        x = _f64(x, (-1, 3)).copy(); v = _f64(v, (-1, 3)).copy(); m = _f64(m, (-1,)).copy(); n = m.shape[0]
+        eta = np.cumsum(m)     # sequential double additions, same as :1266-1279
+        jx = np.zeros_like(x); jv = np.zeros_like(v)
+        P.probe_whfast_c2j(_d(jx), _d(jv), n, _d(x), _d(v), _d(m), _d(eta))
+        out = {"eta": eta.copy(), "jx0": jx.copy(), "jv0": jv.copy()}
+        ids = np.arange(n, dtype=np.int32)
+        assert P.probe_whfast_drift(n, ids.ctypes.data_as(ip), _d(x), _d(v), _d(m), G, _d(jx), _d(jv), _d(eta), dt, 0) == n
+        out["jx1"], out["jv1"] = jx.copy(), jv.copy()
+        x2 = np.empty_like(x); v2 = np.empty_like(v)
+        P.probe_whfast_j2c(_d(x2), _d(v2), n, _d(m), _d(jx), _d(jv), _d(eta))
+        out["x1"], out["v1"] = x2, v2
+        return out
+
+    def stumpff(self, z):
+        c = np.empty(4)
+        self._probe().probe_stumpff(_d(c), float(z))
+        return c
+
     def built_in_system(self, name: str):
         n = C.c_int(); ids = ip(); x = dp(); v = dp(); m = dp(); G = C.c_double()
         rc = self.L.load_built_in_system_python(name.encode(), C.byref(n), C.byref(ids), C.byref(x), C.byref(v), C.byref(m), C.byref(G))
@@ -260,9 +363,11 @@ INTEGRATORS = {"euler": 1, "euler_cromer": 2, "rk4": 3, "leapfrog": 4, "rkf45": 
 
 
 def launch_simulation(lib_path, x, v, m, G, tf, integrator="leapfrog", dt=1e-3, tolerance=1e-9, method="pairwise",
-                      softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=1):
-    """Run launch_simulation_python (src/python_interface.c:94-193) of the given libgrav_sim build with output
-    disabled, exactly as grav_sim/simulator.py:66-102 calls it; returns the final (x, v)."""
+                      softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=1, remove_invalid=False,
+                      full=False, output_dir=None, output_interval=None):
+    """Run launch_simulation_python (src/python_interface.c:94-193) of the given libgrav_sim build exactly as
+    grav_sim/simulator.py:66-102 calls it; returns the final (x, v).  Output is disabled unless output_dir is given
+    (then: CSV snapshots, initial one included, every output_interval, doubles)."""
     L = C.CDLL(str(lib_path))
     x = _f64(x, (-1, 3)).copy(); v = _f64(v, (-1, 3)).copy(); m = _f64(m, (-1,)).copy()
     n = C.c_int32(m.shape[0])
@@ -274,11 +379,16 @@ def launch_simulation(lib_path, x, v, m, G, tf, integrator="leapfrog", dt=1e-3, 
         C.byref(n), ids.ctypes.data_as(C.POINTER(C.c_int32)), _d(x), _d(v), _d(m),
         C.byref(new_ids), C.byref(new_x), C.byref(new_v), C.byref(new_m),
         C.c_double(G), C.c_int32(INTEGRATORS[integrator]), C.c_double(dt), C.c_double(tolerance), C.c_double(-1.0),
-        C.c_bool(False), C.c_int32(METHODS[method]), C.c_double(opening_angle), C.c_double(softening_length),
-        C.c_int32(max_num_particles_per_leaf), C.c_int32(1), b"", C.c_bool(False), C.c_double(tf), C.c_int32(2),
+        C.c_bool(remove_invalid), C.c_int32(METHODS[method]), C.c_double(opening_angle), C.c_double(softening_length),
+        C.c_int32(max_num_particles_per_leaf), C.c_int32(1 if output_dir is None else 2),
+        b"" if output_dir is None else str(output_dir).encode(), C.c_bool(output_dir is not None),
+        C.c_double(tf if output_interval is None else output_interval), C.c_int32(2),
         C.c_int32(2), C.c_int32(2), C.c_int32(0), C.c_bool(False), C.byref(is_exit), C.c_double(tf))
     if rc != 0:
         raise RuntimeError(f"launch_simulation_python -> {rc}")
+    if full:      # whfast reorders (and may remove) particles: n, ids and m change too
+        k = n.value
+        return {"x": x[:k], "v": v[:k], "m": m[:k], "ids": ids[:k]}
     return x, v
 
 

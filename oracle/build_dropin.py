@@ -10,6 +10,9 @@ Composition (exactly what INTEGRATION.md tells a maintainer to do):
     (-DGRAV_SIM_USE_REFERENCE_HEADERS) in their place;
   * src/integrator_whfast.c with a ONE-LINE patch: its static dispatcher whfast_acceleration() forwards to
     grav_b200_shim_whfast_acceleration().  The patched text lives only in a temporary directory.
+  * gravity-simulator_b200/csrc/grav_sim_integrators.c (device-resident leapfrog and WHFast time loops) plus a
+    three-line hook at the top of the reference's leapfrog() (src/integrator.c) and whfast(): the hook runs the
+    resident loop and returns, or declines (GRAV_B200_RESIDENT=0) and lets the reference's own loop run.
   * linked against libgrav_b200.so.
 """
 import re
@@ -24,9 +27,21 @@ REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
 PKG = ROOT / "gravity-simulator_b200"
 OUT = HERE / "_ref" / "libgrav_sim_dropin.so"
 
-KEEP = ["cosmology.c", "error.c", "grav_sim.c", "integrator.c", "integrator_rk_embedded.c", "integrator_ias15.c",
+KEEP = ["cosmology.c", "error.c", "grav_sim.c", "integrator_rk_embedded.c", "integrator_ias15.c",
         "math_functions.c", "output.c", "progress_bar.c", "python_interface.c", "settings.c", "system.c", "utils.c"]
 FLAGS = ["-std=gnu99", "-O3", "-fPIC", "-fopenmp", "-DUSE_OPENMP", '-DVERSION_INFO="0.0.4-b200"', f"-I{REF}/src", f"-I{REF}/pcg", "-w"]
+
+
+def resident_hook(src, definition_regex, hook_fn):
+    """Insert the three-line hook right after the opening brace of a time-loop function's DEFINITION."""
+    m = re.search(definition_regex, src)
+    if not m:
+        raise SystemExit(f"could not locate the definition for {hook_fn} in the reference")
+    hook = (f"\n    extern int {hook_fn}(ErrorStatus *, System *, IntegratorParam *, AccelerationParam *, OutputParam *,"
+            " SimulationStatus *, Settings *, const double);\n"
+            f"    {{ ErrorStatus es_; if ({hook_fn}(&es_, system, integrator_param, acceleration_param, output_param,"
+            " simulation_status, settings, tf)) return es_; }\n")
+    return src[:m.end()] + hook + src[m.end():]
 
 
 def main():
@@ -45,12 +60,18 @@ def main():
             " const double *restrict, const AccelerationParam *);\n"
             "    return grav_b200_shim_whfast_acceleration(a, system, jacobi_x, eta, acceleration_param);\n")
     patched = src[:m.end()] + hook + src[m.end():]
+    patched = resident_hook(patched, r"WIN32DLL_API ErrorStatus whfast\(\s*System \*system,[^)]*\)\s*\{", "grav_b200_shim_whfast")
+    integ = resident_hook((REF / "src" / "integrator.c").read_text(),
+                          r"IN_FILE ErrorStatus leapfrog\(\s*System \*system,[^)]*\)\s*\{", "grav_b200_shim_leapfrog")
     with tempfile.TemporaryDirectory() as tmp:
         pw = Path(tmp) / "integrator_whfast_patched.c"
         pw.write_text(patched)
+        pi = Path(tmp) / "integrator_patched.c"
+        pi.write_text(integ)
         cmd = (["/usr/bin/gcc"] + FLAGS + ["-shared", "-o", str(OUT)] + [str(REF / "src" / f) for f in KEEP]
-               + [str(pw), str(REF / "pcg" / "pcg_basic.c")]
-               + ["-DGRAV_SIM_USE_REFERENCE_HEADERS", f"-I{ROOT}/include", str(PKG / "csrc" / "grav_sim_shim.c")]
+               + [str(pw), str(pi), str(REF / "pcg" / "pcg_basic.c")]
+               + ["-DGRAV_SIM_USE_REFERENCE_HEADERS", f"-I{ROOT}/include", str(PKG / "csrc" / "grav_sim_shim.c"),
+                  str(PKG / "csrc" / "grav_sim_integrators.c")]
                + [f"-L{PKG}", "-lgrav_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../gravity-simulator_b200", "-lm", "-lrt"])
         subprocess.run(cmd, check=True)
     print(f"built {OUT}")

@@ -59,4 +59,24 @@ int oracle_barnes_hut(double *a, int n, const double *x, const double *m, double
 
 /* src/utils.c:27-59 */
 double oracle_energy(int n, const double *x, const double *v, const double *m, double G);
+
+/* ---- WHFast step pieces (whfast_oracle.c), SURVEY.md section 8f row N2 ---- */
+/* src/system.c:1210-1335 (stable by distance from the particle whose id is primary_id); 0 ok, -1 id not found */
+int oracle_sort_by_distance(int n, int *ids, double *x, double *v, double *m, int primary_id);
+/* src/integrator_whfast.c:1266-1279 */
+void oracle_whfast_eta(double *eta, int n, const double *m);
+/* :682-724 and :726-772 */
+void oracle_cartesian_to_jacobi(double *jx, double *jv, int n, const double *x, const double *v, const double *m,
+                                const double *eta);
+void oracle_jacobi_to_cartesian(double *x, double *v, int n, const double *jx, const double *jv, const double *m,
+                                const double *eta);
+/* :774-815, c = {c0, c1, c2, c3} */
+void oracle_stumpff(double c[4], double z);
+/* :424-680; returns the particle count after the removal of invalid particles */
+int oracle_whfast_drift(int n, double *jx, double *jv, int *ids, double *x, double *v, double *m, double *eta, double G,
+                        double dt, int remove_invalid);
+/* :200-407 with output disabled; returns the final particle count (<0: error) */
+int oracle_whfast_integrate(int n, int *ids, double *x, double *v, double *m, double G, double dt, double tf, int method,
+                            double eps, int remove_invalid, int64_t max_steps, int snapshot, double *a_out);
+
 #endif

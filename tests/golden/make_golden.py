@@ -90,3 +90,17 @@ for eps in (0.0, 0.01):
     d[f"a_whfast_massless_eps{eps}"] = R.whfast_acceleration(xs, ms, G, jx9, eta9, "massless", eps)
 np.savez_compressed(OUT / "whfast_solar.npz", **d)
 print("whfast ok")
+
+
+# whole WHFast runs (reference whfast() through oracle/ref_whfast_probe.c, serial removal order)
+import os  # noqa: E402
+os.environ["OMP_NUM_THREADS"] = "1"
+for name, (k, seed, grazers, method, steps, dt, eps) in {
+        "whfast_run_solar": (0, 1, 0, "pairwise", 30, 5.0, 0.0),
+        "whfast_run_belt": (400, 2, 0, "massless", 15, 180.0, 0.0),
+        "whfast_run_removal": (600, 5, 15, "massless", 6, 180.0, 0.0)}.items():
+    x, v, m, G = ics.asteroid_belt(k, seed, grazers=grazers)
+    r = R.whfast_run(x, v, m, G, dt, dt * steps, method, eps, True)
+    np.savez_compressed(OUT / f"{name}.npz", x=x, v=v, m=m, G=np.float64(G), dt=np.float64(dt), steps=np.int64(steps),
+                        method=method, eps=np.float64(eps), out_x=r["x"], out_v=r["v"], out_m=r["m"], out_ids=r["ids"])
+    print(name, "n", m.shape[0], "->", r["m"].shape[0])

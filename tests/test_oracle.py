@@ -97,3 +97,38 @@ def test_fixed_mode_is_more_accurate(oracle, golden):
     fixed = oracle.acceleration(x, m, G, "barnes_hut", eps, 0.5, 1, fixed=True)
     err = lambda a: np.mean(np.linalg.norm(a - exact, axis=1) / np.linalg.norm(exact, axis=1))
     assert err(fixed) < 0.02 < err(ref_mode)
+
+
+# ---- WHFast step pieces (oracle/whfast_oracle.c), SURVEY.md section 8f row N2 -----------------------------------
+@pytest.mark.parametrize("case", ["whfast_run_solar", "whfast_run_belt", "whfast_run_removal"])
+def test_oracle_whfast_run_matches_golden(oracle, golden, case):
+    """Whole whfast() runs minted from the reference (sort, eta, Kepler drift with removal, both transforms, kick)."""
+    g = golden(case)
+    dt, steps = float(g["dt"]), int(g["steps"])
+    o = oracle.whfast_integrate(g["x"], g["v"], g["m"], float(g["G"]), dt, dt * steps, str(g["method"]), float(g["eps"]), True)
+    if case == "whfast_run_removal":
+        assert g["out_m"].shape[0] < g["m"].shape[0]
+    for k in ("x", "v", "m", "ids"):
+        assert np.array_equal(o[k], g[f"out_{k}"], equal_nan=True), (case, k)
+
+
+def test_oracle_whfast_vs_reference_live(oracle, reference, ics, monkeypatch):
+    """Fresh systems through the reference's own whfast() and its static stage functions (ref_whfast_probe.c)."""
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    for k, seed, grazers, method, steps, dt, eps in [(1500, 31, 0, "massless", 8, 180.0, 0.0), (30, 32, 0, "pairwise", 6, 3.0, 0.01),
+                                                     (2500, 33, 60, "massless", 5, 180.0, 0.0)]:
+        x, v, m, G = ics.asteroid_belt(k, seed, grazers=grazers)
+        r = reference.whfast_run(x, v, m, G, dt, dt * steps, method, eps, True)
+        o = oracle.whfast_integrate(x, v, m, G, dt, dt * steps, method, eps, True)
+        assert r["m"].shape == o["m"].shape and (grazers == 0 or r["m"].shape[0] < m.shape[0])
+        for q in ("x", "v", "m", "ids"):
+            assert np.array_equal(r[q], o[q], equal_nan=True), (k, method, q)
+    # stage by stage on a distance-sorted belt
+    x, v, m, G = ics.asteroid_belt(2000, 34)
+    order = np.argsort(np.linalg.norm(x - x[0], axis=1), kind="stable")
+    x, v, m = x[order], v[order], m[order]
+    sr, so = reference.whfast_stages(x, v, m, G, 180.0), oracle.whfast_stages(x, v, m, G, 180.0)
+    for q in sr:
+        assert np.array_equal(sr[q], so[q]), q
+    for z in (0.0, 0.05, -0.09, 0.3, -7.5, 123.456, -1e4, 3e7):
+        assert np.array_equal(reference.stumpff(z), oracle.stumpff(z)), z

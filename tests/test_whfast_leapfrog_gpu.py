@@ -167,3 +167,80 @@ def test_dropin_whfast_massless_belt(ics):
     xr, vr = launch_simulation(ref, x, v, m, G, **kw)
     xd, vd = launch_simulation(dropin, x, v, m, G, **kw)
     assert np.array_equal(xd, xr) and np.array_equal(vd, vr)
+
+
+# ---- device-resident time loops behind the reference's leapfrog() / whfast() (grav_sim_integrators.c) ------------
+@pytest.fixture
+def resident_off(monkeypatch):
+    monkeypatch.setenv("GRAV_B200_RESIDENT", "0")
+
+
+def test_dropin_host_loop_leapfrog_still_works(ics, resident_off):
+    """GRAV_B200_RESIDENT=0: the hook declines and the reference's own leapfrog loop calls acceleration() per step."""
+    from oracle.bind import launch_simulation
+    dropin, ref = _dropin()
+    x, v, m, G = ics.two_plummer(400, seed=3)
+    kw = dict(tf=0.01, integrator="leapfrog", dt=1e-3, method="barnes_hut", softening_length=0.0, opening_angle=0.5)
+    xr, vr = launch_simulation(ref, x, v, m, G, **kw)
+    xd, vd = launch_simulation(dropin, x, v, m, G, **kw)
+    assert np.array_equal(xd, xr) and np.array_equal(vd, vr)
+
+
+def test_dropin_host_loop_whfast_still_works(ics, resident_off):
+    from oracle.bind import launch_simulation
+    dropin, ref = _dropin()
+    x, v, m, G = ics.asteroid_belt(300, 4)
+    kw = dict(tf=180.0 * 6, integrator="whfast", dt=180.0, method="massless", full=True)
+    r = launch_simulation(ref, x, v, m, G, **kw)
+    d = launch_simulation(dropin, x, v, m, G, **kw)
+    for k in ("x", "v", "m", "ids"):
+        assert np.array_equal(d[k], r[k]), k
+
+
+def _read_snapshots(path):
+    files = sorted(p for p in path.rglob("*.csv"))
+    # the initial snapshot is written before simulation_status is initialised (src/integrator.c:944-960 vs :996-998):
+    # its "# time" / "# dt" header lines print uninitialised stack memory in every build, so they are not compared
+    keep = lambda name, ln: not (name.endswith("00000.csv") and (ln.startswith("# time") or ln.startswith("# dt")))
+    return [(p.name, [ln for ln in p.read_text().splitlines() if keep(p.name, ln)]) for p in files]
+
+
+@pytest.mark.parametrize("integrator,method,dt,steps,interval", [
+    ("whfast", "massless", 180.0, 9, 400.0),         # outputs between steps: the -dt/2 snapshot convention (:346-351)
+    ("leapfrog", "barnes_hut", 1e-3, 12, 2.5e-3),
+    ("leapfrog", "pairwise", 1e-3, 7, 3e-3),         # tf is not a multiple of the interval
+])
+def test_dropin_resident_snapshots_match_reference(ics, tmp_path, integrator, method, dt, steps, interval):
+    """CSV snapshots written by the reference build and by the drop-in build with the resident time loop: same files,
+    same particle order, same digits (the CSV prints 17 significant digits); and the same final state."""
+    from oracle.bind import launch_simulation
+    dropin, ref = _dropin()
+    if integrator == "whfast":
+        x, v, m, G = ics.asteroid_belt(400, 8)
+        tol = 0.0
+    else:
+        x, v, m, G = ics.two_plummer(300, seed=4)
+        tol = 0.0 if method == "barnes_hut" else 1e-11
+    outs = {}
+    for name, lib in (("ref", ref), ("dropin", dropin)):
+        d = tmp_path / name
+        d.mkdir()
+        kw = dict(tf=dt * steps, integrator=integrator, dt=dt, method=method, opening_angle=0.5, full=True,
+                  output_dir=str(d) + "/", output_interval=interval)
+        outs[name] = (launch_simulation(lib, x, v, m, G, **kw), _read_snapshots(d))
+    (fr, sr), (fd, sd) = outs["ref"], outs["dropin"]
+    assert len(sr) >= 3 and [n for n, _ in sr] == [n for n, _ in sd]
+    for (_, a), (_, b) in zip(sr, sd):
+        assert len(a) == len(b)
+        if tol == 0.0:
+            assert a == b
+        else:
+            num = lambda ls: np.array([[float(t) for t in ln.split(",")] for ln in ls if ln[0] not in "#p"])
+            assert [ln for ln in a if ln[0] in "#p"] == [ln for ln in b if ln[0] in "#p"]
+            assert np.allclose(num(a), num(b), rtol=tol, atol=tol)
+    for k in ("ids", "m"):
+        assert np.array_equal(fd[k], fr[k])
+    if tol == 0.0:
+        assert np.array_equal(fd["x"], fr["x"]) and np.array_equal(fd["v"], fr["v"])
+    else:
+        assert max_rel_err(fd["x"], fr["x"]) <= tol and max_rel_err(fd["v"], fr["v"]) <= 1e-9

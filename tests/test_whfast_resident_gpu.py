@@ -1,0 +1,110 @@
+"""Device-resident WHFast against the oracle's restatement of whfast()
+(oracle/whfast_oracle.c, pinned bit-exact against the reference in tests/test_oracle.py): all arithmetic is IEEE in
+the reference's order, so every comparison is np.array_equal -- particle order and ids included."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(got, ref):
+    assert got["ids"].shape == ref["ids"].shape, (got["ids"].shape, ref["ids"].shape)
+    for k in ("ids", "m", "x", "v"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), (k, np.nanmax(np.abs(got[k] - ref[k])))
+
+
+def _run_gpu(gb, x, v, m, G, dt, steps, method, eps, remove, chunks=(None,), ids=None):
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.whfast_begin(dt, method, eps, remove, ids=ids)
+        left = steps
+        for ch in chunks:
+            k = left if ch is None else min(ch, left)
+            c.whfast_steps(dt, k)
+            left -= k
+        assert left == 0
+        out = c.whfast_state(snapshot=False)
+        c.whfast_end()
+    return out
+
+
+@pytest.mark.parametrize("k,seed,steps,method,eps,dt", [
+    (0, 1, 40, "pairwise", 0.0, 5.0),          # config 1's system, every body massive
+    (0, 1, 25, "massless", 0.0, 5.0),
+    (60, 2, 8, "pairwise", 0.01, 2.0),         # massless particles through the all-pairs kernel, softened
+    (500, 3, 20, "massless", 0.0, 180.0),
+    (5000, 4, 12, "massless", 0.0, 180.0),
+    (20000, 5, 70, "massless", 0.0, 30.0),     # several optimistic batches
+])
+def test_resident_whfast_matches_oracle(gb, oracle, ics, k, seed, steps, method, eps, dt):
+    x, v, m, G = ics.asteroid_belt(k, seed)
+    ref = oracle.whfast_integrate(x, v, m, G, dt, dt * steps, method, eps, True)
+    got = _run_gpu(gb, x, v, m, G, dt, steps, method, eps, True, chunks=(3, 1, None))
+    _same(got, ref)
+
+
+def test_resident_whfast_config3_size(gb, oracle, ics):
+    """Config 3 at its full size: Sun + 8 planets + 1e5 massless asteroids, dt = 180 d."""
+    x, v, m, G = ics.asteroid_belt(100000, 7)
+    ref = oracle.whfast_integrate(x, v, m, G, 180.0, 180.0 * 5, "massless", 0.0, True)
+    got = _run_gpu(gb, x, v, m, G, 180.0, 5, "massless", 0.0, True)
+    _same(got, ref)
+
+
+@pytest.mark.parametrize("k,grazers,seed,steps", [(2000, 40, 5, 6), (7000, 100, 6, 4), (3000, 25, 9, 40)])
+def test_resident_whfast_removes_invalid_particles(gb, oracle, ics, k, grazers, seed, steps):
+    """Kepler solves that fail flag particles for removal (:551); the optimistic batch is replayed and the flagged step
+    finished with a stable compaction -- same survivors, same order, same state as the serial reference."""
+    x, v, m, G = ics.asteroid_belt(k, seed, grazers=grazers)
+    ref = oracle.whfast_integrate(x, v, m, G, 180.0, 180.0 * steps, "massless", 0.0, True)
+    assert ref["m"].shape[0] < m.shape[0]                      # the case does remove particles
+    got = _run_gpu(gb, x, v, m, G, 180.0, steps, "massless", 0.0, True)
+    _same(got, ref)
+
+
+def test_resident_whfast_without_removal(gb, oracle, ics):
+    """whfast_remove_invalid_particles = false: no checkpoints, no replays, one long queue of steps."""
+    x, v, m, G = ics.asteroid_belt(3000, 21)
+    ref = oracle.whfast_integrate(x, v, m, G, 60.0, 60.0 * 50, "massless", 0.0, False)
+    got = _run_gpu(gb, x, v, m, G, 60.0, 50, "massless", 0.0, False)
+    _same(got, ref)
+
+
+def test_resident_whfast_snapshot_convention(gb, oracle, ics):
+    """snapshot=True: v kicked back by -dt/2 through a second Jacobi->Cartesian conversion (:346-351); the reference
+    leaves system->x/v in that state, and continues from the untouched Jacobi state."""
+    x, v, m, G = ics.asteroid_belt(800, 11)
+    dt = 90.0
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.whfast_begin(dt, "massless", 0.0, True)
+        c.whfast_steps(dt, 6)
+        half = c.whfast_state(snapshot=False)
+        snap = c.whfast_state(snapshot=True)
+        c.whfast_steps(dt, 4)
+        end = c.whfast_state(snapshot=False)
+    r6 = oracle.whfast_integrate(x, v, m, G, dt, dt * 6, "massless", 0.0, True)
+    _same(half, r6)
+    _same(snap, oracle.whfast_integrate(x, v, m, G, dt, dt * 6, "massless", 0.0, True, snapshot=True))
+    assert np.array_equal(snap["x"], half["x"]) and not np.array_equal(snap["v"], half["v"])
+    _same(end, oracle.whfast_integrate(x, v, m, G, dt, dt * 10, "massless", 0.0, True))
+
+
+def test_resident_whfast_ids_and_errors(gb, oracle, ics):
+    x, v, m, G = ics.asteroid_belt(300, 13)
+    n = m.shape[0]
+    perm = np.random.default_rng(1).permutation(n)           # shuffled input order: the Sun (id 0) is not at index 0,
+    assert perm[0] != 0                                      # so the primary is found by search (src/system.c:1241-1251)
+    xs, vs, ms, ids = x[perm].copy(), v[perm].copy(), m[perm].copy(), perm.astype(np.int32)
+    ref = oracle.whfast_integrate(xs, vs, ms, G, 100.0, 500.0, "massless", 0.0, True, ids=ids)
+    assert ref["ids"][0] == 0 and ref["m"].shape[0] == n
+    got = _run_gpu(gb, xs, vs, ms, G, 100.0, 5, "massless", 0.0, True, ids=ids)
+    _same(got, ref)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        with pytest.raises(gb.GravB200Error, match="Only pairwise and massless"):
+            c.whfast_begin(1.0, "barnes_hut")
+        with pytest.raises(gb.GravB200Error, match="Primary particle ID not found"):
+            c.whfast_begin(1.0, "massless", ids=np.arange(1, n + 1, dtype=np.int32))
+        with pytest.raises(gb.GravB200Error, match="whfast_begin"):
+            c.whfast_steps(1.0, 1)

@@ -121,10 +121,13 @@ constexpr int SORT_BITS = 8;
 constexpr int SORT_RADIX = 1 << SORT_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ROUNDS = 16;                              // pairs per thread
-constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;        // 4096 pairs per CTA
-constexpr int SORT_WCHUNK = 32 * SORT_ROUNDS;                // 512 pairs per warp
-constexpr size_t SORT_SMEM = (size_t)SORT_TILE * (sizeof(long long) + sizeof(int));   // staging: 48 KiB
+constexpr int SORT_ROUNDS = 16;                              // pairs per thread: 4096-pair tiles (large n)
+constexpr int SORT_ROUNDS_SMALL = 4;                         // 1024-pair tiles, n <= SORT_SMALL_MAX_N
+constexpr int SORT_SMALL_MAX_N = 128 * SORT_THREADS * SORT_ROUNDS_SMALL;   // <= 128 tiles: every CTA scans the histogram itself
+// Small-n variant (FUSED): a 1e5-particle sort has only 25 of the big tiles -- a sixth of the SMs -- and its three scan
+// launches per pass cost more than the sort kernels.  With 1024-pair tiles the work spreads over ~100 CTAs, the histogram
+// is laid out [tile][digit] and each scatter CTA derives its own output offsets from it (<= 128 x 256 counters, read
+// coalesced from L2), so a pass is two launches instead of five.
 
 __device__ __forceinline__ unsigned match_digit(int d, bool valid)
 {
@@ -143,16 +146,18 @@ __device__ __forceinline__ unsigned match_digit(int d, bool valid)
 }
 __device__ __forceinline__ int digit_of(long long k, int shift) { return (int)((unsigned long long)k >> shift) & (SORT_RADIX - 1); }
 
+template <int ROUNDS, bool FUSED>
 __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const long long *__restrict__ keys, int n, int shift,
                                                                  int num_tiles, int *__restrict__ hist)
 {
+    constexpr int SORT_TILE = SORT_THREADS * ROUNDS;
     __shared__ int cnt[SORT_RADIX];
     cnt[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * SORT_TILE;
     const int lane = threadIdx.x & 31;
 #pragma unroll 4
-    for (int r = 0; r < SORT_ROUNDS; r++) {
+    for (int r = 0; r < ROUNDS; r++) {
         const int p = base + r * SORT_THREADS + threadIdx.x;      // order is irrelevant for counting: coalesced
         const bool valid = p < n;
         const int d = valid ? digit_of(keys[p], shift) : SORT_RADIX;
@@ -160,15 +165,20 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const long long
         if (valid && (same >> lane) == 1u) atomicAdd(&cnt[d], __popc(same));   // one atomic per distinct digit per warp
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * num_tiles + blockIdx.x] = cnt[threadIdx.x];
+    if (FUSED) hist[(size_t)blockIdx.x * SORT_RADIX + threadIdx.x] = cnt[threadIdx.x];
+    else hist[(size_t)threadIdx.x * num_tiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
+template <int ROUNDS, bool FUSED>
 __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const long long *__restrict__ keys_in,
                                                                     const int *__restrict__ vals_in, int n, int shift,
                                                                     int num_tiles, const int *__restrict__ offs,
                                                                     long long *__restrict__ keys_out,
                                                                     int *__restrict__ vals_out)
 {
+    constexpr int SORT_ROUNDS = ROUNDS;
+    constexpr int SORT_TILE = SORT_THREADS * ROUNDS;
+    constexpr int SORT_WCHUNK = 32 * ROUNDS;
     extern __shared__ __align__(16) unsigned char sort_smem[];
     long long *skeys = reinterpret_cast<long long *>(sort_smem);
     int *svals = reinterpret_cast<int *>(sort_smem + (size_t)SORT_TILE * sizeof(long long));
@@ -225,7 +235,31 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const long l
         const int dstart = woff + inc - run;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; w++) wcnt[w][d] += dstart;
-        gbase[d] = offs[(size_t)d * num_tiles + blockIdx.x] - dstart;
+        if (!FUSED) {
+            gbase[d] = offs[(size_t)d * num_tiles + blockIdx.x] - dstart;
+        } else {
+            // offs is the raw [tile][digit] histogram: first output slot of (d, this tile) = pairs with a smaller digit
+            // anywhere + pairs with this digit in earlier tiles
+            int tot = 0, before = 0;
+            for (int t = 0; t < num_tiles; t++) {
+                const int h = offs[(size_t)t * SORT_RADIX + d];
+                tot += h;
+                if (t < (int)blockIdx.x) before += h;
+            }
+            int ginc = tot;
+#pragma unroll
+            for (int s2 = 1; s2 < 32; s2 <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, ginc, s2);
+                if (lane >= s2) ginc += t;
+            }
+            __syncthreads();                   // wsum is reused
+            if (lane == 31) wsum[warp] = ginc;
+            __syncthreads();
+            int goff = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; w++) goff += (w < warp) ? wsum[w] : 0;
+            gbase[d] = goff + ginc - tot + before - dstart;
+        }
     }
     __syncthreads();
 
@@ -260,18 +294,33 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const long l
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift)
 {
     DevTree &t = c->tree;
+    constexpr int TILE_BIG = SORT_THREADS * SORT_ROUNDS, TILE_SMALL = SORT_THREADS * SORT_ROUNDS_SMALL;
+    constexpr size_t SMEM_BIG = (size_t)TILE_BIG * (sizeof(long long) + sizeof(int));       // staging: 48 KiB
+    constexpr size_t SMEM_SMALL = (size_t)TILE_SMALL * (sizeof(long long) + sizeof(int));   // 12 KiB
     static bool attr_set = false;
     if (!attr_set) {
-        GB_CUDA(cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM));
+        GB_CUDA(cudaFuncSetAttribute(sort_scatter_kernel<SORT_ROUNDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BIG));
         attr_set = true;
     }
-    const int num_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    if (n <= SORT_SMALL_MAX_N) {
+        const int num_tiles = (n + TILE_SMALL - 1) / TILE_SMALL;
+        GB_TRY(t.hist.reserve(sizeof(int) * (size_t)SORT_RADIX * num_tiles));
+        sort_hist_kernel<SORT_ROUNDS_SMALL, true><<<num_tiles, SORT_THREADS, 0, c->stream>>>(kin, n, shift, num_tiles, t.hist.as<int>());
+        GB_LAUNCH_CHECK();
+        sort_scatter_kernel<SORT_ROUNDS_SMALL, true><<<num_tiles, SORT_THREADS, SMEM_SMALL, c->stream>>>(kin, vin, n, shift, num_tiles,
+                                                                                                      t.hist.as<int>(), kout, vout);
+        GB_LAUNCH_CHECK();
+        count_launch(2);
+        return GRAV_B200_OK;
+    }
+    const int num_tiles = (n + TILE_BIG - 1) / TILE_BIG;
     GB_TRY(t.hist.reserve(sizeof(int) * (size_t)SORT_RADIX * num_tiles));
-    sort_hist_kernel<<<num_tiles, SORT_THREADS, 0, c->stream>>>(kin, n, shift, num_tiles, t.hist.as<int>());
+    sort_hist_kernel<SORT_ROUNDS, false><<<num_tiles, SORT_THREADS, 0, c->stream>>>(kin, n, shift, num_tiles, t.hist.as<int>());
     GB_LAUNCH_CHECK();
     count_launch();
     GB_TRY(exclusive_scan_int(c, t.hist.as<int>(), t.hist.as<int>(), SORT_RADIX * num_tiles, t.scan_tmp));
-    sort_scatter_kernel<<<num_tiles, SORT_THREADS, SORT_SMEM, c->stream>>>(kin, vin, n, shift, num_tiles, t.hist.as<int>(), kout, vout);
+    sort_scatter_kernel<SORT_ROUNDS, false><<<num_tiles, SORT_THREADS, SMEM_BIG, c->stream>>>(kin, vin, n, shift, num_tiles,
+                                                                                             t.hist.as<int>(), kout, vout);
     GB_LAUNCH_CHECK();
     count_launch();
     return GRAV_B200_OK;

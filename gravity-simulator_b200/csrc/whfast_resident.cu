@@ -51,6 +51,11 @@ struct WhfastState {
     DevBuf ck_jx, ck_jv, ck_m, ck_ids;       // checkpoint of the Jacobi state at the start of a batch
     int *h_status = nullptr;                 // pinned
     int K = 0;                               // massive particles
+    // two consecutive steps captured as one CUDA graph (the ping-pong buffers are back in place after two), per
+    // starting parity; valid for one (n, K, dt)
+    cudaGraphExec_t pair_exec[2] = {nullptr, nullptr};
+    int pair_n[2] = {0, 0}, pair_K[2] = {0, 0}, pair_launches[2] = {0, 0};
+    double pair_dt[2] = {0.0, 0.0};
     int method = 0;
     double eps = 0.0;
     bool remove_invalid = false;
@@ -72,6 +77,7 @@ void whfast_state_free(grav_b200_ctx *c)
                       &w->cstate, &w->texp, &w->bad, &w->status, &w->ck_jx, &w->ck_jv, &w->ck_m, &w->ck_ids};
     for (DevBuf *b : bufs) b->release();
     if (w->h_status) cudaFreeHost(w->h_status);
+    for (int k = 0; k < 2; k++) if (w->pair_exec[k]) cudaGraphExecDestroy(w->pair_exec[k]);
     delete w;
     c->wh = nullptr;
 }
@@ -142,9 +148,11 @@ __global__ void wh_list_kernel(int n, const int *__restrict__ flag, const int *_
 }
 
 // eta over the massive particles only (:1266-1279): etaM[k] = eta[list[k]]
-__global__ void wh_eta_skel_kernel(int K, const int *__restrict__ list, const double *__restrict__ m, double *__restrict__ etaM)
+__global__ void wh_eta_skel_kernel(int K, const int *__restrict__ list, const double *__restrict__ m, double *__restrict__ etaM,
+                                   int *__restrict__ status)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    status[5] += 1;          // step tag for the drift kernel that follows (kernel parameters are frozen inside a graph)
     double e = 0.0;
     for (int k = 0; k < K; k++) {
         const double mk = m[list[k]];
@@ -194,7 +202,7 @@ __device__ __forceinline__ void stumpff(double z, double &c0, double &c1, double
 __global__ void __launch_bounds__(128) wh_drift_kernel(int n, double *__restrict__ jx, double *__restrict__ jv,
                                                        const double *__restrict__ m, const int *__restrict__ rank,
                                                        const double *__restrict__ etaM, double *__restrict__ eta, double G,
-                                                       double dt, int remove_invalid, int step_tag, char *__restrict__ bad,
+                                                       double dt, int remove_invalid, char *__restrict__ bad,
                                                        int *__restrict__ status)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(128) wh_drift_kernel(int n, double *__restrict
         const double err = dvd(sub(add(add(mul(mul(xn, s), c1), mul(mul(xr, ss), c2)), mul(mul(gm, mul(ss, s)), c3)), dt), r);
         if ((err > 1e-5 || z_bad) && remove_invalid) {                                                  // :551
             bad[i] = 1;
-            atomicMin(&status[1], step_tag);
+            atomicMin(&status[1], status[5] - 1);
             atomicAdd(&status[2], 1);
         }
     }
@@ -453,7 +461,7 @@ static int wh_reserve(grav_b200_ctx *c, WhfastState *w, int n)
     GB_TRY(w->status.reserve(sizeof(int) * 8));
     GB_TRY(w->ck_jx.reserve(b3)); GB_TRY(w->ck_jv.reserve(b3)); GB_TRY(w->ck_m.reserve(b1));
     GB_TRY(w->ck_ids.reserve(sizeof(int) * (size_t)n));
-    if (!w->h_status) GB_CUDA(cudaMallocHost(&w->h_status, sizeof(int) * 8));
+    if (!w->h_status) GB_CUDA(cudaMallocHost(&w->h_status, sizeof(int) * 16));
     return GRAV_B200_OK;
 }
 
@@ -501,7 +509,7 @@ static int wh_massive(grav_b200_ctx *c, WhfastState *w, bool count_massive)
     }
     wh_list_kernel<<<WH_GRID(n, 256)>>>(n, flag, rank, w->list.as<int>());
     WH_LAUNCHED();
-    wh_eta_skel_kernel<<<1, 32, 0, c->stream>>>(w->K, w->list.as<int>(), w->M(), w->etaM.as<double>());
+    wh_eta_skel_kernel<<<1, 32, 0, c->stream>>>(w->K, w->list.as<int>(), w->M(), w->etaM.as<double>(), w->status.as<int>());
     WH_LAUNCHED();
     return GRAV_B200_OK;
 }
@@ -539,12 +547,12 @@ static int wh_check_status(grav_b200_ctx *c, WhfastState *w)
 }
 
 // front half of a step: sort, eta, drift (:299-327 without the removal)
-static int wh_step_front(grav_b200_ctx *c, WhfastState *w, double dt, int step_tag)
+static int wh_step_front(grav_b200_ctx *c, WhfastState *w, double dt)
 {
     GB_TRY(wh_sort(c, w));
     GB_TRY(wh_massive(c, w, false));
     wh_drift_kernel<<<WH_GRID(c->n, 128)>>>(c->n, w->JX(), w->JV(), w->M(), w->rank.as<int>(), w->etaM.as<double>(),
-                                            w->eta.as<double>(), c->G, dt, w->remove_invalid ? 1 : 0, step_tag, w->bad.as<char>(),
+                                            w->eta.as<double>(), c->G, dt, w->remove_invalid ? 1 : 0, w->bad.as<char>(),
                                             w->status.as<int>());
     WH_LAUNCHED();
     return GRAV_B200_OK;
@@ -555,6 +563,52 @@ static int wh_step_back(grav_b200_ctx *c, WhfastState *w, double dt)
     GB_TRY(wh_j2c(c, w, w->JV()));
     GB_TRY(wh_accel_kick(c, w, dt));
     w->last_dt = dt;
+    return GRAV_B200_OK;
+}
+
+// Two steps as one graph launch.  The first use with a given (parity, n, K, dt) captures the launches of two ordinary
+// steps from the stream; every buffer already has its final size by then (at least one plain step has run).
+static int wh_step_pair(grav_b200_ctx *c, WhfastState *w, double dt)
+{
+    const int par = w->cur;
+    if (!w->pair_exec[par] || w->pair_n[par] != c->n || w->pair_K[par] != w->K || w->pair_dt[par] != dt) {
+        if (w->pair_exec[par]) { cudaGraphExecDestroy(w->pair_exec[par]); w->pair_exec[par] = nullptr; }
+        const int64_t l0 = g_launch_count;
+        GB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = wh_step_front(c, w, dt);
+        if (rc == GRAV_B200_OK) rc = wh_step_back(c, w, dt);
+        if (rc == GRAV_B200_OK) rc = wh_step_front(c, w, dt);
+        if (rc == GRAV_B200_OK) rc = wh_step_back(c, w, dt);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        const int captured = (int)(g_launch_count - l0);
+        __atomic_fetch_sub(&g_launch_count, (int64_t)captured, __ATOMIC_RELAXED);      // nothing ran yet
+        if (rc != GRAV_B200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        GB_CUDA(e);
+        const cudaError_t ei = cudaGraphInstantiate(&w->pair_exec[par], graph, 0);
+        cudaGraphDestroy(graph);
+        GB_CUDA(ei);
+        w->pair_n[par] = c->n; w->pair_K[par] = w->K; w->pair_dt[par] = dt; w->pair_launches[par] = captured;
+    }
+    GB_CUDA(cudaGraphLaunch(w->pair_exec[par], c->stream));
+    count_launch(w->pair_launches[par]);
+    w->last_dt = dt;
+    return GRAV_B200_OK;
+}
+
+static int wh_steps_plain_or_graph(grav_b200_ctx *c, WhfastState *w, double dt, int count, bool use_graph)
+{
+    int s = 0;
+    if (use_graph && count >= 3) {
+        GB_TRY(wh_step_front(c, w, dt));       // sizes every scratch buffer for this n before a capture
+        GB_TRY(wh_step_back(c, w, dt));
+        s = 1;
+        for (; s + 2 <= count; s += 2) GB_TRY(wh_step_pair(c, w, dt));
+    }
+    for (; s < count; s++) {
+        GB_TRY(wh_step_front(c, w, dt));
+        GB_TRY(wh_step_back(c, w, dt));
+    }
     return GRAV_B200_OK;
 }
 
@@ -586,8 +640,9 @@ static int wh_remove_flagged(grav_b200_ctx *c, WhfastState *w, int n_removed)
 
 static int wh_reset_batch_status(grav_b200_ctx *c, WhfastState *w)
 {
-    w->h_status[0] = 0; w->h_status[1] = WH_NO_BAD; w->h_status[2] = 0; w->h_status[3] = 0;
-    GB_CUDA(cudaMemcpyAsync(w->status.as<int>(), w->h_status, sizeof(int) * 4, cudaMemcpyHostToDevice, c->stream));
+    // constants only: the pinned words may still be in flight from an earlier reset
+    w->h_status[8] = 0; w->h_status[9] = WH_NO_BAD; w->h_status[10] = 0; w->h_status[11] = 0; w->h_status[12] = 0; w->h_status[13] = 0;
+    GB_CUDA(cudaMemcpyAsync(w->status.as<int>(), w->h_status + 8, sizeof(int) * 6, cudaMemcpyHostToDevice, c->stream));
     return GRAV_B200_OK;
 }
 static int wh_read_status(grav_b200_ctx *c, WhfastState *w)
@@ -669,6 +724,8 @@ int grav_b200_ctx_whfast_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
     if (!w || !w->ready) { set_error("whfast_begin() has not been called"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     int64_t remaining = num_steps;
+    const char *genv = getenv("GRAV_B200_WHFAST_GRAPH");
+    const bool use_graph = !(genv && genv[0] == '0');
     while (remaining > 0) {
         const int B = (int)(remaining < WH_BATCH ? remaining : WH_BATCH);
         const int n = c->n;
@@ -679,10 +736,7 @@ int grav_b200_ctx_whfast_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
             GB_CUDA(cudaMemcpyAsync(w->ck_ids.p, w->IDS(), sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         }
         GB_TRY(wh_reset_batch_status(c, w));
-        for (int s = 0; s < B; s++) {
-            GB_TRY(wh_step_front(c, w, dt, s));
-            GB_TRY(wh_step_back(c, w, dt));
-        }
+        GB_TRY(wh_steps_plain_or_graph(c, w, dt, B, use_graph));
         GB_TRY(wh_read_status(c, w));
         const int first_bad = w->h_status[1];
         if (!w->remove_invalid || first_bad == WH_NO_BAD) { remaining -= B; continue; }
@@ -692,12 +746,9 @@ int grav_b200_ctx_whfast_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
         GB_CUDA(cudaMemcpyAsync(w->M(), w->ck_m.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         GB_CUDA(cudaMemcpyAsync(w->IDS(), w->ck_ids.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         GB_TRY(wh_reset_batch_status(c, w));
-        for (int s = 0; s < first_bad; s++) {
-            GB_TRY(wh_step_front(c, w, dt, WH_NO_BAD - 1));
-            GB_TRY(wh_step_back(c, w, dt));
-        }
+        GB_TRY(wh_steps_plain_or_graph(c, w, dt, first_bad, use_graph));
         GB_TRY(wh_reset_batch_status(c, w));
-        GB_TRY(wh_step_front(c, w, dt, 0));
+        GB_TRY(wh_step_front(c, w, dt));
         GB_TRY(wh_read_status(c, w));
         const int n_removed = w->h_status[2];
         if (n_removed <= 0 || n_removed >= n) { set_error("whfast replay lost the flagged particles (%d of %d)", n_removed, n); return GRAV_B200_ECUDA; }

@@ -51,6 +51,8 @@ def parse_args():
     p.add_argument("--eps", type=float, default=0.01)
     p.add_argument("--ic", default="plummer", choices=["plummer", "uniform"])
     p.add_argument("--bh-n", type=int, default=1 << 20, help="particles of the Barnes-Hut side measurement (0 = skip)")
+    p.add_argument("--whfast-n", type=int, default=100000,
+                   help="massless asteroids of the WHFast side measurement (config 3; 0 = skip; single GPU only)")
     p.add_argument("--cpu-n", type=int, default=1 << 16, help="particles of the bounded CPU-baseline sample (0 = skip)")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -325,9 +327,70 @@ def run_b200_arm(args):
             bh = {"metric": "barnes_hut_force_eval_s_per_step", "value": bh_ms * 1e-3, "unit": "s", "n": args.bh_n,
                   "theta": 0.5, "leaf": 1, "ic": args.ic, "mode": "reference-exact",
                   "stage_ms": {"gather": st[0], "bbox_morton": st[1], "sort": st[2], "build": st[3], "walk": st[4]},
-                  "hbm_frac_algorithmic": (470.0 * args.bh_n / (bh_ms * 1e-3) / 1e9) / _hbm_peak()}
+                  "hbm_frac_algorithmic": (470.0 * args.bh_n / (bh_ms * 1e-3) / 1e9) / _hbm_peak(),
+                  # algorithmic bytes per particle of each stage over the stage time and the HBM peak
+                  "stage_hbm_frac": {k: (b * args.bh_n / (max(t_ms, 1e-6) * 1e-3) / 1e9) / _hbm_peak()
+                                     for k, b, t_ms in (("bbox_morton", 60.0, st[1]), ("sort", 204.0, st[2]),
+                                                        ("build", 79.0, st[3]), ("walk", 127.0, st[4]))},
+                  "stage_bytes_per_particle": {"bbox_morton": 60, "sort": 204, "build": 79, "walk": 127}}
         except gb.GravB200Error as e:
             bh = {"unavailable": str(e)[:200]}
+
+    # massless direct sum at config 3's size: HBM streaming, in practice launch-latency bound
+    ml = None
+    if args.whfast_n > 0 and world == 1:
+        try:
+            from gravity_simulator_b200 import ics as _ics
+            xw, vw, mw, Gw = _ics.asteroid_belt(args.whfast_n, 7)
+            ctx.set_system(xw, mw, Gw, vw)
+            for _ in range(3):
+                ctx.acceleration("massless", 0.0)
+            ctx.synchronize()
+            reps = 20
+            ctx.event_record(6)
+            for _ in range(reps):
+                ctx.acceleration("massless", 0.0)
+            ctx.event_record(7)
+            ml_ms = ctx.event_elapsed_ms(6, 7) / reps
+            nb = int(mw.shape[0])
+            ml = {"metric": "massless_force_eval_ms", "value": ml_ms, "unit": "ms", "n": nb, "massive": int((mw != 0).sum()),
+                  "algorithmic_bytes": 56 * nb, "achieved_GBps": 56.0 * nb / (ml_ms * 1e-3) / 1e9,
+                  "hbm_frac": (56.0 * nb / (ml_ms * 1e-3) / 1e9) / _hbm_peak(),
+                  "note": "9 x 1e5 interactions: a few launches of ~us each, bound by launch latency, not HBM"}
+        except gb.GravB200Error as e:
+            ml = {"unavailable": str(e)[:200]}
+
+    # WHFast side measurement (config 3): device-resident steps vs the reference's whfast() on the host cores
+    wh = None
+    if args.whfast_n > 0 and world == 1:
+        try:
+            from gravity_simulator_b200 import ics as _ics
+            xw, vw, mw, Gw = _ics.asteroid_belt(args.whfast_n, 7)
+            dtw, ksteps = 180.0, 200
+            ctx.set_system(xw, mw, Gw, vw)
+            ctx.whfast_begin(dtw, "massless", 0.0, True)
+            ctx.whfast_steps(dtw, 9)
+            ctx.synchronize()
+            l0 = gb.kernel_launch_count()
+            ctx.event_record(4)
+            ctx.whfast_steps(dtw, ksteps)
+            ctx.event_record(5)
+            wh_ms = ctx.event_elapsed_ms(4, 5) / ksteps
+            wh = {"metric": "whfast_steps_per_s", "value": 1e3 / wh_ms, "unit": "steps/s", "ms_per_step": wh_ms,
+                  "n": int(mw.shape[0]), "massive": int((mw != 0).sum()), "dt_days": dtw, "acceleration": "massless",
+                  "remove_invalid_particles": True, "launches_per_step": (gb.kernel_launch_count() - l0) / ksteps,
+                  "state": "device-resident (sort, eta, Kepler drift, Jacobi transforms, acceleration, kick); bit-identical to the reference"}
+            ctx.whfast_end()
+            from oracle.bind import Reference
+            if Reference.available():
+                R = Reference()
+                t0 = time.perf_counter()
+                R.whfast_run(xw, vw, mw, Gw, dtw, dtw * 10, "massless", 0.0, False)
+                wh["cpu_reference_ms_per_step"] = (time.perf_counter() - t0) / 10 * 1e3
+                wh["cpu_reference_note"] = (f"the reference's whfast() (OpenMP build, {os.cpu_count()} host cores; its sort and both "
+                                            "coordinate transforms are serial), 10 steps")
+        except gb.GravB200Error as e:
+            wh = {"unavailable": str(e)[:200]}
 
     cpu = None
     if rank == 0 and args.cpu_n > 0:
@@ -346,7 +409,7 @@ def run_b200_arm(args):
                        "partition": f"targets sharded over {world} rank(s), NCCL all-gather of positions per step" if world > 1 else "single GPU",
                        "l2": "256 MiB L2 flush between timed iterations"},
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "bh": bh, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "bh": bh, "massless": ml, "whfast": wh, "gpu_launches": int(launches),
             "clocks": clocks, "allgather_ms": float(np.mean(gather_ms)) if world > 1 else 0.0,
         }
         print(json.dumps(line), flush=True)

@@ -104,7 +104,7 @@ ABI_SYMBOLS = [
     "grav_b200_kernel_launch_count", "grav_b200_measure_fp64_peak", "grav_b200_ctx_event_record",
     "grav_b200_ctx_event_elapsed_ms", "grav_b200_ctx_flush_l2", "grav_b200_ctx_mark_positions_sharded",
     "grav_b200_host_register", "grav_b200_host_unregister",
-    "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
+    "grav_b200_compute_energy", "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
 ]
 SHIM_SYMBOLS = [
     "get_new_acceleration_param", "finalize_acceleration_param", "acceleration", "acceleration_barnes_hut",
@@ -169,6 +169,7 @@ def load():
     wh = [c_double_p, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, C.c_double]
     abi.grav_b200_whfast_acceleration_pairwise.argtypes = wh
     abi.grav_b200_whfast_acceleration_massless.argtypes = wh
+    abi.grav_b200_compute_energy.argtypes = [c_double_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double]
     abi.grav_b200_morton_keys.argtypes = [C.c_int, c_double_p, c_int64_p, c_double_p, c_double_p]
 
     shim.get_new_acceleration_param.restype = AccelerationParam
@@ -311,6 +312,15 @@ def morton_keys(x):
     width = np.empty(1)
     check_rc(abi.grav_b200_morton_keys(x.shape[0], _dp(x), keys.ctypes.data_as(c_int64_p), _dp(center), _dp(width)))
     return keys, center, float(width[0])
+
+
+def compute_energy(x, v, m, G) -> float:
+    """compute_energy (src/utils.c:27-59) on the GPU through the one-shot C ABI."""
+    abi, _ = load()
+    x = as_f64(x).reshape(-1, 3); v = as_f64(v).reshape(-1, 3); m = as_f64(m).reshape(-1)
+    e = C.c_double()
+    check_rc(abi.grav_b200_compute_energy(C.byref(e), m.shape[0], _dp(x), _dp(v), _dp(m), float(G)))
+    return e.value
 
 
 def device_count() -> int:

@@ -464,6 +464,17 @@ int grav_b200_acceleration_barnes_hut(double *a, int n, const double *x, const d
     return one_shot(a, n, x, m, G, GRAV_B200_METHOD_BARNES_HUT, eps, theta, leaf);
 }
 
+int grav_b200_compute_energy(double *energy, int n, const double *x, const double *v, const double *m, double G)
+{
+    if (!energy || !v) { set_error("NULL array pointer"); return GRAV_B200_EINVAL; }
+    GB_TRY(check_sys(energy, n, x, m));
+    std::lock_guard<std::mutex> lk(g_mu);
+    grav_b200_ctx *c;
+    GB_TRY(default_ctx(&c));
+    GB_TRY(grav_b200_ctx_set_system(c, n, x, v, m, G));
+    return grav_b200_ctx_energy(c, energy);
+}
+
 static int whfast_one_shot(double *a, int n, const double *x, const double *m, double G, const double *jx,
                            const double *eta, double eps, bool massless)
 {

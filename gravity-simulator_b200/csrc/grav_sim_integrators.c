@@ -2,6 +2,9 @@
  * grav_sim_integrators.c -- device-resident time loops for the two fixed-step integrators whose every sub-step
  * is on the hot path: leapfrog (config 2 and 4) and WHFast (config 3).  Plain C, reference-facing.
  *
+ * Also here: the hook for the O(N^2) energy diagnostic (compute_energy, src/utils.c:27-59; compute_energy_python,
+ * src/python_interface.c:195-243), which at config 2/3 sizes costs more than many integration steps on the host.
+ *
  * Compiled ONLY inside the reference tree (it uses the reference's IntegratorParam / OutputParam /
  * SimulationStatus / Settings, output_snapshot() and the progress bar as they are -- INTEGRATION.md section 1),
  * together with two three-line hooks at the top of the reference's own leapfrog() (src/integrator.c:894) and
@@ -20,6 +23,7 @@
  */
 #include <math.h>
 #include <stdbool.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -301,5 +305,62 @@ done:
         grav_b200_ctx_destroy(ctx);
     }
     *out = error_status;
+    return 1;
+}
+
+/* ---- energy diagnostic (src/utils.c:27-59, src/python_interface.c:195-243) ------------------------------------ */
+
+#define ENERGY_MIN_PARTICLES 1024   /* below this the host pair loop takes microseconds; the hook declines */
+
+/* Hook at the top of compute_energy():  { double e_; if (grav_b200_shim_compute_energy(&e_, system)) return e_; } */
+int grav_b200_shim_compute_energy(double *energy, const System *system)
+{
+    if (!resident_enabled() || system->num_particles < ENERGY_MIN_PARTICLES)
+    {
+        return 0;
+    }
+    const int rc = grav_b200_compute_energy(energy, system->num_particles, system->x, system->v, system->m, system->G);
+    if (rc != GRAV_B200_OK)
+    {
+        /* compute_energy() has no error channel: fail loudly instead of silently taking another path */
+        fprintf(stderr, "compute_energy (B200): %s\n", grav_b200_last_error());
+        *energy = NAN;
+    }
+    return 1;
+}
+
+/* Hook at the top of compute_energy_python(): snapshots are packed [m, x, y, z, vx, vy, vz] per particle. */
+int grav_b200_shim_compute_energy_python(double *energy, const double G, const double *sol_state, const int num_snapshots,
+                                         const int num_particles)
+{
+    if (!resident_enabled() || num_particles < ENERGY_MIN_PARTICLES)
+    {
+        return 0;
+    }
+    double *buf = malloc(sizeof(double) * 7 * (size_t) num_particles);
+    if (!buf)
+    {
+        return 0;
+    }
+    double *x = buf, *v = buf + 3 * (size_t) num_particles, *m = buf + 6 * (size_t) num_particles;
+    for (int s = 0; s < num_snapshots; s++)
+    {
+        const double *snap = sol_state + (size_t) s * 7 * (size_t) num_particles;
+        for (int i = 0; i < num_particles; i++)
+        {
+            m[i] = snap[i * 7 + 0];
+            for (int k = 0; k < 3; k++)
+            {
+                x[i * 3 + k] = snap[i * 7 + 1 + k];
+                v[i * 3 + k] = snap[i * 7 + 4 + k];
+            }
+        }
+        if (grav_b200_compute_energy(&energy[s], num_particles, x, v, m, G) != GRAV_B200_OK)
+        {
+            fprintf(stderr, "compute_energy_python (B200): %s\n", grav_b200_last_error());
+            energy[s] = NAN;
+        }
+    }
+    free(buf);
     return 1;
 }

@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__
             const double4 q = tile[j];
             const double dx = q.x - me.x, dy = q.y - me.y, dz = q.z - me.z;
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            // padding has m = 0; the self term (and exact coincidences) have r2 = 0: skip both
-            if (r2 > 0.0 && (j0 + j) < n) pot += q.w / sqrt(r2);
+            // skip padding and the self term only: coincident particles give inf / NaN like the reference's 1/0
+            if ((j0 + j) < n && (j0 + j) != i) pot += q.w / sqrt(r2);
         }
     }
     double e = 0.0;

@@ -73,6 +73,11 @@ int grav_b200_acceleration_barnes_hut(double *a, int n, const double *x, const d
                                       double G, double softening_length,
                                       double opening_angle, int max_num_particles_per_leaf);
 
+/* replaces the O(N^2) pair loop of compute_energy, src/utils.c:27-59 (and of compute_energy_python,
+ * src/python_interface.c:195-243, per snapshot): sum_i m_i |v_i|^2 / 2 - G sum_{i<j} m_i m_j / |x_i - x_j|,
+ * unsoftened.  Summation order differs from the serial loop: agrees to ~1e-13 relative. */
+int grav_b200_compute_energy(double *energy, int n, const double *x, const double *v, const double *m, double G);
+
 /* replaces whfast_acceleration_pairwise / _massless, src/integrator_whfast.c:839-957, 959-1264
  * jacobi_x[3n], eta[n] as computed by the WHFast caller.  Softening is r^3 + eps^3 here. */
 int grav_b200_whfast_acceleration_pairwise(double *a, int n, const double *x, const double *m,

@@ -13,6 +13,8 @@ Composition (exactly what INTEGRATION.md tells a maintainer to do):
   * gravity-simulator_b200/csrc/grav_sim_integrators.c (device-resident leapfrog and WHFast time loops) plus a
     three-line hook at the top of the reference's leapfrog() (src/integrator.c) and whfast(): the hook runs the
     resident loop and returns, or declines (GRAV_B200_RESIDENT=0) and lets the reference's own loop run.
+  * the same kind of hook at the top of compute_energy() (src/utils.c) and compute_energy_python()
+    (src/python_interface.c): the O(N^2) potential sum runs on the GPU for N >= 1024.
   * linked against libgrav_b200.so.
 """
 import re
@@ -28,8 +30,15 @@ PKG = ROOT / "gravity-simulator_b200"
 OUT = HERE / "_ref" / "libgrav_sim_dropin.so"
 
 KEEP = ["cosmology.c", "error.c", "grav_sim.c", "integrator_rk_embedded.c", "integrator_ias15.c",
-        "math_functions.c", "output.c", "progress_bar.c", "python_interface.c", "settings.c", "system.c", "utils.c"]
+        "math_functions.c", "output.c", "progress_bar.c", "settings.c", "system.c"]
 FLAGS = ["-std=gnu99", "-O3", "-fPIC", "-fopenmp", "-DUSE_OPENMP", '-DVERSION_INFO="0.0.4-b200"', f"-I{REF}/src", f"-I{REF}/pcg", "-w"]
+
+
+def simple_hook(src, definition_regex, text):
+    m = re.search(definition_regex, src)
+    if not m:
+        raise SystemExit(f"could not locate {definition_regex!r} in the reference")
+    return src[:m.end()] + "\n" + text + src[m.end():]
 
 
 def resident_hook(src, definition_regex, hook_fn):
@@ -63,13 +72,25 @@ def main():
     patched = resident_hook(patched, r"WIN32DLL_API ErrorStatus whfast\(\s*System \*system,[^)]*\)\s*\{", "grav_b200_shim_whfast")
     integ = resident_hook((REF / "src" / "integrator.c").read_text(),
                           r"IN_FILE ErrorStatus leapfrog\(\s*System \*system,[^)]*\)\s*\{", "grav_b200_shim_leapfrog")
+    utils = simple_hook((REF / "src" / "utils.c").read_text(),
+                        r"WIN32DLL_API double compute_energy\(const System \*restrict system\)\s*\{",
+                        "    extern int grav_b200_shim_compute_energy(double *, const System *);\n"
+                        "    { double e_; if (grav_b200_shim_compute_energy(&e_, system)) return e_; }\n")
+    pyif = simple_hook((REF / "src" / "python_interface.c").read_text(),
+                       r"WIN32DLL_API void compute_energy_python\([^)]*\)\s*\{",
+                       "    extern int grav_b200_shim_compute_energy_python(double *, const double, const double *, const int, const int);\n"
+                       "    if (grav_b200_shim_compute_energy_python(energy, G, sol_state, num_snapshots, num_particles)) return;\n")
     with tempfile.TemporaryDirectory() as tmp:
         pw = Path(tmp) / "integrator_whfast_patched.c"
         pw.write_text(patched)
         pi = Path(tmp) / "integrator_patched.c"
         pi.write_text(integ)
+        pu = Path(tmp) / "utils_patched.c"
+        pu.write_text(utils)
+        pp = Path(tmp) / "python_interface_patched.c"
+        pp.write_text(pyif)
         cmd = (["/usr/bin/gcc"] + FLAGS + ["-shared", "-o", str(OUT)] + [str(REF / "src" / f) for f in KEEP]
-               + [str(pw), str(pi), str(REF / "pcg" / "pcg_basic.c")]
+               + [str(pw), str(pi), str(pu), str(pp), str(REF / "pcg" / "pcg_basic.c")]
                + ["-DGRAV_SIM_USE_REFERENCE_HEADERS", f"-I{ROOT}/include", str(PKG / "csrc" / "grav_sim_shim.c"),
                   str(PKG / "csrc" / "grav_sim_integrators.c")]
                + [f"-L{PKG}", "-lgrav_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../gravity-simulator_b200", "-lm", "-lrt"])

@@ -244,3 +244,35 @@ def test_dropin_resident_snapshots_match_reference(ics, tmp_path, integrator, me
         assert np.array_equal(fd["x"], fr["x"]) and np.array_equal(fd["v"], fr["v"])
     else:
         assert max_rel_err(fd["x"], fr["x"]) <= tol and max_rel_err(fd["v"], fr["v"]) <= 1e-9
+
+
+# ---- energy diagnostic through the one-shot C ABI and the drop-in hooks (src/utils.c:27-59) -----------------------
+def test_compute_energy_one_shot(gb, reference, ics):
+    for x, v, m, G in (ics.plummer(3000, 5), ics.asteroid_belt(2000, 6)):
+        e, e_ref = gb.compute_energy(x, v, m, G), reference.energy(x, v, m, G)
+        assert abs(e - e_ref) <= 1e-12 * abs(e_ref)
+    x, v, m, G = ics.plummer(1500, 7)
+    x[10] = x[900]                                    # coincident pair: the reference divides by zero -> -inf
+    assert gb.compute_energy(x, v, m, G) == reference.energy(x, v, m, G) == -np.inf
+
+
+def test_dropin_energy_hooks(ics, reference):
+    """compute_energy() / compute_energy_python() of the drop-in build (hooked, N >= 1024) against the reference build."""
+    import ctypes as C
+    from oracle.bind import RefSystem, dp, _d
+    dropin, ref = _dropin()
+    x, v, m, G = ics.plummer(4096, 8)
+    L = C.CDLL(str(dropin))
+    L.compute_energy.restype = C.c_double
+    s = RefSystem(num_particles=m.shape[0], particle_ids=None, x=_d(x), v=_d(v), m=_d(m), G=G)
+    e_ref = reference.energy(x, v, m, G)
+    assert abs(L.compute_energy(C.byref(s)) - e_ref) <= 1e-12 * abs(e_ref)
+    # two packed snapshots [m, x, v] per particle
+    snap = np.concatenate([m[:, None], x, v], axis=1)
+    sol = np.ascontiguousarray(np.stack([snap, snap * np.array([1, 1, 1, 1, 0.5, 0.5, 0.5])]))
+    out = np.zeros(2)
+    L.compute_energy_python.restype = None
+    L.compute_energy_python(_d(out), C.c_double(G), _d(sol), C.c_int32(2), C.c_int32(m.shape[0]))
+    assert abs(out[0] - e_ref) <= 1e-12 * abs(e_ref)
+    e2 = reference.energy(x, 0.5 * v, m, G)
+    assert abs(out[1] - e2) <= 1e-12 * abs(e2)

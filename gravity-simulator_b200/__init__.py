@@ -104,7 +104,7 @@ ABI_SYMBOLS = [
     "grav_b200_kernel_launch_count", "grav_b200_measure_fp64_peak", "grav_b200_ctx_event_record",
     "grav_b200_ctx_event_elapsed_ms", "grav_b200_ctx_flush_l2", "grav_b200_ctx_mark_positions_sharded",
     "grav_b200_host_register", "grav_b200_host_unregister",
-    "grav_b200_compute_energy", "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
+    "grav_b200_compute_energy", "grav_b200_ctx_fixed_begin", "grav_b200_ctx_fixed_steps", "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
 ]
 SHIM_SYMBOLS = [
     "get_new_acceleration_param", "finalize_acceleration_param", "acceleration", "acceleration_barnes_hut",
@@ -148,6 +148,8 @@ def load():
     abi.grav_b200_ctx_leapfrog_end.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_leapfrog_steps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
     abi.grav_b200_ctx_energy.argtypes = [C.c_void_p, c_double_p]
+    abi.grav_b200_ctx_fixed_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    abi.grav_b200_ctx_fixed_steps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
     abi.grav_b200_ctx_whfast_begin.argtypes = [C.c_void_p, c_int_p, C.c_int, C.c_double, C.c_double, C.c_int]
     abi.grav_b200_ctx_whfast_steps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
     abi.grav_b200_ctx_whfast_get_state.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p]
@@ -401,6 +403,16 @@ class Context:
 
     def leapfrog_steps(self, dt, num_steps):
         check_rc(self.abi.grav_b200_ctx_leapfrog_steps(self.h, float(dt), int(num_steps)))
+
+    # Euler / Euler-Cromer / RK4 on the resident state (src/integrator.c:281-892)
+    def fixed_begin(self, integrator, method="pairwise", softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=-1):
+        code = {"euler": 1, "euler_cromer": 2, "rk4": 3}[integrator] if isinstance(integrator, str) else int(integrator)
+        meth = METHODS[method] if isinstance(method, str) else int(method)
+        check_rc(self.abi.grav_b200_ctx_fixed_begin(self.h, code, meth, float(softening_length), float(opening_angle),
+                                                    int(max_num_particles_per_leaf)))
+
+    def fixed_steps(self, dt, num_steps):
+        check_rc(self.abi.grav_b200_ctx_fixed_steps(self.h, float(dt), int(num_steps)))
 
     # device-resident WHFast (src/integrator_whfast.c:200-407)
     def whfast_begin(self, dt, method="massless", softening_length=0.0, remove_invalid_particles=True, ids=None):

@@ -228,7 +228,7 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     whfast_state_free(c);
     comm_destroy(c);
     DevBuf *bufs[] = {&c->posm, &c->vel, &c->acc, &c->xcomp, &c->vcomp, &c->stage_a, &c->stage_b, &c->stage_c, &c->stage_d,
-                      &c->partials, &c->misc, &c->msrc, &c->msrc_id, &c->msrc_altm, &c->l2_flush, &c->mflag, &c->mrank};
+                      &c->partials, &c->misc, &c->rk_buf, &c->msrc, &c->msrc_id, &c->msrc_altm, &c->l2_flush, &c->mflag, &c->mrank};
     for (DevBuf *b : bufs) b->release();
     DevTree &t = c->tree;
     DevBuf *tb[] = {&t.keys_unsorted, &t.keys, &t.perm, &t.keys_tmp, &t.perm_tmp, &t.hist, &t.bbox, &t.exp_rec,
@@ -265,6 +265,7 @@ int grav_b200_ctx_set_system(grav_b200_ctx *c, int n, const double *x, const dou
     c->lo = (int)(((long long)c->rank * n) / c->world);
     c->hi = (int)(((long long)(c->rank + 1) * n) / c->world);
     c->lf_ready = false;
+    c->fixed_integrator = 0;
     const size_t b3 = sizeof(double) * 3 * (size_t)n;
     GB_TRY(c->posm.reserve(sizeof(double4) * (size_t)c->n_pad));
     GB_TRY(c->acc.reserve(b3));

@@ -1,14 +1,15 @@
 /*
- * grav_sim_integrators.c -- device-resident time loops for the two fixed-step integrators whose every sub-step
- * is on the hot path: leapfrog (config 2 and 4) and WHFast (config 3).  Plain C, reference-facing.
+ * grav_sim_integrators.c -- device-resident time loops for the fixed-step integrators whose every sub-step is on
+ * the hot path: leapfrog (config 2 and 4), WHFast (config 3) and Euler / Euler-Cromer / RK4.  Plain C,
+ * reference-facing.
  *
  * Also here: the hook for the O(N^2) energy diagnostic (compute_energy, src/utils.c:27-59; compute_energy_python,
  * src/python_interface.c:195-243), which at config 2/3 sizes costs more than many integration steps on the host.
  *
  * Compiled ONLY inside the reference tree (it uses the reference's IntegratorParam / OutputParam /
  * SimulationStatus / Settings, output_snapshot() and the progress bar as they are -- INTEGRATION.md section 1),
- * together with two three-line hooks at the top of the reference's own leapfrog() (src/integrator.c:894) and
- * whfast() (src/integrator_whfast.c:200):
+ * together with a three-line hook at the top of the reference's own leapfrog(), euler(), euler_cromer(), rk4()
+ * (src/integrator.c:894, :281, :456, :630) and whfast() (src/integrator_whfast.c:200):
  *
  *     { ErrorStatus es_; if (grav_b200_shim_whfast(&es_, system, integrator_param, acceleration_param,
  *                                                  output_param, simulation_status, settings, tf)) return es_; }
@@ -306,6 +307,137 @@ done:
     }
     *out = error_status;
     return 1;
+}
+
+
+/* ---- Euler, Euler-Cromer, RK4 (src/integrator.c:281-454, :456-628, :630-892) --------------------------------- */
+
+static int fixed_step_resident(ErrorStatus *out, const int integrator, System *system, IntegratorParam *integrator_param,
+                               AccelerationParam *acceleration_param, OutputParam *output_param,
+                               SimulationStatus *simulation_status, Settings *settings, const double tf)
+{
+    if (!resident_enabled())
+    {
+        return 0;
+    }
+    const int method = acceleration_param->method;
+    if (method != ACCELERATION_METHOD_PAIRWISE && method != ACCELERATION_METHOD_MASSLESS &&
+        method != ACCELERATION_METHOD_BARNES_HUT)
+    {
+        return 0;
+    }
+
+    ErrorStatus error_status = make_success_error_status();
+    grav_b200_ctx *ctx = NULL;
+    double dt = integrator_param->dt;
+    const bool is_output = (output_param->method != OUTPUT_METHOD_DISABLED);
+    const double output_interval = output_param->output_interval;
+    double next_output_time = output_interval;
+    const bool enable_progress_bar = settings->enable_progress_bar;
+    const bool check_overshoot = (integrator != GRAV_B200_INTEGRATOR_RK4);   /* rk4() has no overshoot check (:736-741) */
+    ProgressBarParam progress_bar_param;
+    int64 queued = 0;
+    double queued_dt = dt;
+
+    if (is_output && output_param->output_initial)
+    {
+        TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
+    }
+    TRY_RC(grav_b200_ctx_create(&ctx, resident_device(), 0, 1, NULL));
+    TRY_RC(grav_b200_ctx_set_system(ctx, system->num_particles, system->x, system->v, system->m, system->G));
+    TRY_RC(grav_b200_ctx_fixed_begin(ctx, integrator, method, acceleration_param->softening_length,
+                                     acceleration_param->opening_angle, acceleration_param->max_num_particles_per_leaf));
+
+    const int64 total_num_steps = (int64) ceil(tf / dt);
+    if (enable_progress_bar)
+    {
+        TRY_STATUS(start_progress_bar(&progress_bar_param, total_num_steps));
+    }
+    simulation_status->t = 0.0;
+    simulation_status->dt = dt;
+    simulation_status->num_steps = 0;
+    while (simulation_status->num_steps < total_num_steps)
+    {
+        if (check_overshoot)
+        {
+            if (simulation_status->t + dt > tf)
+            {
+                dt = tf - simulation_status->t;
+            }
+            simulation_status->dt = dt;
+        }
+        if (queued > 0 && dt != queued_dt)
+        {
+            TRY_RC(grav_b200_ctx_fixed_steps(ctx, queued_dt, queued));
+            queued = 0;
+        }
+        queued_dt = dt;
+        queued++;
+
+        (simulation_status->num_steps)++;
+        simulation_status->t = (simulation_status->num_steps) * dt;
+
+        const bool output_due = is_output && simulation_status->t >= next_output_time;
+        const bool leaving = *(settings->is_exit_ptr) || simulation_status->num_steps == total_num_steps;
+        if (output_due || leaving || queued >= RESIDENT_MAX_QUEUED_STEPS)
+        {
+            TRY_RC(grav_b200_ctx_fixed_steps(ctx, queued_dt, queued));
+            queued = 0;
+        }
+        if (output_due)
+        {
+            TRY_RC(grav_b200_ctx_get_positions(ctx, system->x));
+            TRY_RC(grav_b200_ctx_get_velocities(ctx, system->v));
+            TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
+            next_output_time = (output_param->output_count_) * output_interval;
+        }
+        if (enable_progress_bar)
+        {
+            update_progress_bar(&progress_bar_param, simulation_status->num_steps, false);
+        }
+        if (*(settings->is_exit_ptr))
+        {
+            break;
+        }
+    }
+    TRY_RC(grav_b200_ctx_get_positions(ctx, system->x));
+    TRY_RC(grav_b200_ctx_get_velocities(ctx, system->v));
+    if (enable_progress_bar)
+    {
+        update_progress_bar(&progress_bar_param, simulation_status->num_steps, true);
+    }
+
+done:
+    if (ctx)
+    {
+        grav_b200_ctx_destroy(ctx);
+    }
+    *out = error_status;
+    return 1;
+}
+
+int grav_b200_shim_euler(ErrorStatus *out, System *system, IntegratorParam *integrator_param,
+                         AccelerationParam *acceleration_param, OutputParam *output_param,
+                         SimulationStatus *simulation_status, Settings *settings, const double tf)
+{
+    return fixed_step_resident(out, GRAV_B200_INTEGRATOR_EULER, system, integrator_param, acceleration_param, output_param,
+                               simulation_status, settings, tf);
+}
+
+int grav_b200_shim_euler_cromer(ErrorStatus *out, System *system, IntegratorParam *integrator_param,
+                                AccelerationParam *acceleration_param, OutputParam *output_param,
+                                SimulationStatus *simulation_status, Settings *settings, const double tf)
+{
+    return fixed_step_resident(out, GRAV_B200_INTEGRATOR_EULER_CROMER, system, integrator_param, acceleration_param,
+                               output_param, simulation_status, settings, tf);
+}
+
+int grav_b200_shim_rk4(ErrorStatus *out, System *system, IntegratorParam *integrator_param,
+                       AccelerationParam *acceleration_param, OutputParam *output_param,
+                       SimulationStatus *simulation_status, Settings *settings, const double tf)
+{
+    return fixed_step_resident(out, GRAV_B200_INTEGRATOR_RK4, system, integrator_param, acceleration_param, output_param,
+                               simulation_status, settings, tf);
 }
 
 /* ---- energy diagnostic (src/utils.c:27-59, src/python_interface.c:195-243) ------------------------------------ */

@@ -58,6 +58,95 @@ __global__ void __launch_bounds__(256) vsync_kernel(const double *__restrict__ v
     out[k] = __dsub_rn(v[k], __dmul_rn(__dmul_rn(0.5, a[k]), dt));
 }
 
+
+// ---- Euler, Euler-Cromer, RK4 (src/integrator.c:281-454, :456-628, :630-892) ---------------------------------------
+// Same conventions as the leapfrog kernels: the reference's formulas and association, IEEE without contraction, one
+// thread per owned particle.  mode 0: Euler (x and v advance from the old v and a, :382-395); mode 1: Euler-Cromer
+// (v first, x with the NEW v, :557-569).
+__global__ void __launch_bounds__(256) euler_kernel(double4 *__restrict__ posm, double *__restrict__ vel, const double *__restrict__ acc,
+                                                   double *__restrict__ xc, double *__restrict__ vc, int lo, int hi, double dt, int cromer)
+{
+    const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    double4 q = posm[i];
+    double x0[3] = {q.x, q.y, q.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const size_t e = 3 * (size_t)i + k;
+        const double v0 = vel[e], a = acc[e];
+        double cv = __dadd_rn(vc[e], __dmul_rn(a, dt));
+        const double v1 = __dadd_rn(v0, cv);
+        cv = __dadd_rn(cv, __dsub_rn(v0, v1));
+        double cx = __dadd_rn(xc[e], __dmul_rn(cromer ? v1 : v0, dt));
+        const double x1 = __dadd_rn(x0[k], cx);
+        cx = __dadd_rn(cx, __dsub_rn(x0[k], x1));
+        vel[e] = v1; vc[e] = cv; xc[e] = cx;
+        x0[k] = x1;
+    }
+    q.x = x0[0]; q.y = x0[1]; q.z = x0[2];
+    posm[i] = q;
+}
+
+// RK4 stage s = 1..3 (:746-819): record xk_s = v and vk_s = a, then x = x_0 + [0.5] xk_s dt, v = v_0 + [0.5] vk_s dt.
+// Stage 1 also stores x_0, v_0 (:742-743).
+__global__ void __launch_bounds__(256) rk4_stage_kernel(double4 *__restrict__ posm, double *__restrict__ vel, const double *__restrict__ acc,
+                                                       double *__restrict__ x_0, double *__restrict__ v_0, double *__restrict__ xk,
+                                                       double *__restrict__ vk, int lo, int hi, double dt, int stage)
+{
+    const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    double4 q = posm[i];
+    double xs[3] = {q.x, q.y, q.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const size_t e = 3 * (size_t)i + k;
+        const double v = vel[e], a = acc[e];
+        if (stage == 1) { x_0[e] = xs[k]; v_0[e] = v; }
+        xk[e] = v; vk[e] = a;
+        const double bx = x_0[e], bv = v_0[e];
+        if (stage < 3) {
+            xs[k] = __dadd_rn(bx, __dmul_rn(__dmul_rn(0.5, v), dt));
+            vel[e] = __dadd_rn(bv, __dmul_rn(__dmul_rn(0.5, a), dt));
+        } else {
+            xs[k] = __dadd_rn(bx, __dmul_rn(v, dt));
+            vel[e] = __dadd_rn(bv, __dmul_rn(a, dt));
+        }
+    }
+    q.x = xs[0]; q.y = xs[1]; q.z = xs[2];
+    posm[i] = q;
+}
+
+// RK4 update (:837-850): xk4 = v, vk4 = a, weighted sum through the compensated-summation terms.
+__global__ void __launch_bounds__(256) rk4_final_kernel(double4 *__restrict__ posm, double *__restrict__ vel, const double *__restrict__ acc,
+                                                       const double *__restrict__ x_0, const double *__restrict__ v_0,
+                                                       const double *__restrict__ xk1, const double *__restrict__ xk2,
+                                                       const double *__restrict__ xk3, const double *__restrict__ vk1,
+                                                       const double *__restrict__ vk2, const double *__restrict__ vk3,
+                                                       double *__restrict__ xc, double *__restrict__ vc, int lo, int hi, double dt)
+{
+    const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    double4 q = posm[i];
+    double xs[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const size_t e = 3 * (size_t)i + k;
+        const double xk4 = vel[e], vk4 = acc[e];
+        const double sv = __dadd_rn(__dadd_rn(__dadd_rn(vk1[e], __dmul_rn(2.0, vk2[e])), __dmul_rn(2.0, vk3[e])), vk4);
+        const double sx = __dadd_rn(__dadd_rn(__dadd_rn(xk1[e], __dmul_rn(2.0, xk2[e])), __dmul_rn(2.0, xk3[e])), xk4);
+        double cv = __dadd_rn(vc[e], __ddiv_rn(__dmul_rn(sv, dt), 6.0));
+        double cx = __dadd_rn(xc[e], __ddiv_rn(__dmul_rn(sx, dt), 6.0));
+        const double bv = v_0[e], bx = x_0[e];
+        const double v1 = __dadd_rn(bv, cv), x1 = __dadd_rn(bx, cx);
+        cv = __dadd_rn(cv, __dsub_rn(bv, v1));
+        cx = __dadd_rn(cx, __dsub_rn(bx, x1));
+        vel[e] = v1; vc[e] = cv; xc[e] = cx;
+        xs[k] = x1;
+    }
+    q.x = xs[0]; q.y = xs[1]; q.z = xs[2];
+    posm[i] = q;
+}
+
 static int run_force(grav_b200_ctx *c)
 {
     return grav_b200_ctx_acceleration(c, c->lf_method, c->lf_eps, c->lf_theta, c->lf_leaf);
@@ -194,6 +283,73 @@ int grav_b200_ctx_leapfrog_end(grav_b200_ctx *c)
         count_launch();
     }
     c->lf_ready = false;
+    return GRAV_B200_OK;
+}
+
+
+int grav_b200_ctx_fixed_begin(grav_b200_ctx *c, int integrator, int method, double eps, double theta, int max_leaf)
+{
+    if (!c || c->n < 1) { set_error("context has no system"); return GRAV_B200_EINVAL; }
+    if (integrator != GRAV_B200_INTEGRATOR_EULER && integrator != GRAV_B200_INTEGRATOR_EULER_CROMER &&
+        integrator != GRAV_B200_INTEGRATOR_RK4) {
+        set_error("Unknown fixed-step integrator. Got: %d", integrator);
+        return GRAV_B200_EINVAL;
+    }
+    GB_CUDA(cudaSetDevice(c->device));
+    const size_t b3 = sizeof(double) * 3 * (size_t)c->n;
+    GB_TRY(c->xcomp.reserve(b3));
+    GB_TRY(c->vcomp.reserve(b3));
+    GB_CUDA(cudaMemsetAsync(c->xcomp.p, 0, b3, c->stream));     // calloc'ed error terms (:313-314, :488-489, :672-673)
+    GB_CUDA(cudaMemsetAsync(c->vcomp.p, 0, b3, c->stream));
+    if (integrator == GRAV_B200_INTEGRATOR_RK4) GB_TRY(c->rk_buf.reserve(8 * b3));   // x_0, v_0, xk1-3, vk1-3
+    c->lf_method = method; c->lf_eps = eps; c->lf_theta = theta; c->lf_leaf = max_leaf;
+    c->lf_ready = false;
+    c->fixed_integrator = integrator;
+    return GRAV_B200_OK;
+}
+
+int grav_b200_ctx_fixed_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
+{
+    if (!c || !c->fixed_integrator) { set_error("fixed_begin() has not been called"); return GRAV_B200_EINVAL; }
+    GB_CUDA(cudaSetDevice(c->device));
+    const int cnt = c->hi - c->lo;
+    const unsigned blocks = (unsigned)((cnt + 255) / 256);
+    double4 *posm = c->posm.as<double4>();
+    double *vel = c->vel.as<double>(), *acc = c->acc.as<double>(), *xc = c->xcomp.as<double>(), *vc = c->vcomp.as<double>();
+    const size_t n3 = 3 * (size_t)c->n;
+    for (int64_t s = 0; s < num_steps; s++) {
+        if (c->fixed_integrator != GRAV_B200_INTEGRATOR_RK4) {
+            GB_TRY(run_force(c));
+            if (cnt > 0) {
+                euler_kernel<<<blocks, 256, 0, c->stream>>>(posm, vel, acc, xc, vc, c->lo, c->hi, dt,
+                                                           c->fixed_integrator == GRAV_B200_INTEGRATOR_EULER_CROMER);
+                GB_LAUNCH_CHECK();
+                count_launch();
+            }
+            if (c->world > 1) c->posm_gathered = false;
+            continue;
+        }
+        double *r = c->rk_buf.as<double>();
+        double *x_0 = r, *v_0 = r + n3, *xk = r + 2 * n3, *vk = r + 5 * n3;     // xk[3][n3], vk[3][n3]
+        for (int st = 1; st <= 3; st++) {
+            GB_TRY(run_force(c));
+            if (cnt > 0) {
+                rk4_stage_kernel<<<blocks, 256, 0, c->stream>>>(posm, vel, acc, x_0, v_0, xk + (st - 1) * n3, vk + (st - 1) * n3,
+                                                               c->lo, c->hi, dt, st);
+                GB_LAUNCH_CHECK();
+                count_launch();
+            }
+            if (c->world > 1) c->posm_gathered = false;
+        }
+        GB_TRY(run_force(c));
+        if (cnt > 0) {
+            rk4_final_kernel<<<blocks, 256, 0, c->stream>>>(posm, vel, acc, x_0, v_0, xk, xk + n3, xk + 2 * n3, vk, vk + n3, vk + 2 * n3,
+                                                           xc, vc, c->lo, c->hi, dt);
+            GB_LAUNCH_CHECK();
+            count_launch();
+        }
+        if (c->world > 1) c->posm_gathered = false;
+    }
     return GRAV_B200_OK;
 }
 

@@ -121,6 +121,8 @@ struct grav_b200_ctx {
     int lf_method = 0, lf_leaf = 1;
     double lf_eps = 0.0, lf_theta = 1.0, lf_dt = 0.0;
     bool lf_ready = false;
+    int fixed_integrator = 0;     // Euler / Euler-Cromer / RK4 on the resident state (integrate.cu)
+    gb::DevBuf rk_buf;            // RK4: x_0, v_0, xk1..3, vk1..3
 
     void *wh = nullptr;   // gb::WhfastState (whfast_resident.cu)
 

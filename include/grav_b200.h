@@ -158,6 +158,17 @@ int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *ctx, int method, double softenin
 int grav_b200_ctx_leapfrog_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
 int grav_b200_ctx_leapfrog_end(grav_b200_ctx *ctx);
 
+/* Euler, Euler-Cromer and RK4 on the resident state; mirror euler(), euler_cromer() and rk4(), src/integrator.c:281-454,
+ * :456-628, :630-892 (same update formulas, compensated summation and operation order).  fixed_begin() zeroes the
+ * error terms and fixes the force parameters; fixed_steps() advances num_steps steps of size dt (one force evaluation
+ * per step, four for RK4).  Positions/velocities are read back with get_positions()/get_velocities(). */
+#define GRAV_B200_INTEGRATOR_EULER        1   /* src/integrator.h:17-19 */
+#define GRAV_B200_INTEGRATOR_EULER_CROMER 2
+#define GRAV_B200_INTEGRATOR_RK4          3
+int grav_b200_ctx_fixed_begin(grav_b200_ctx *ctx, int integrator, int method, double softening_length,
+                              double opening_angle, int max_num_particles_per_leaf);
+int grav_b200_ctx_fixed_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
+
 /* Device-resident WHFast on the resident state (one GPU); mirrors whfast(), src/integrator_whfast.c:200-407, with
  * the particle order, eta, the Kepler drift, both coordinate transforms and the kick on the device -- bit-identical
  * to the reference after any number of steps.

@@ -11,7 +11,8 @@ Composition (exactly what INTEGRATION.md tells a maintainer to do):
   * src/integrator_whfast.c with a ONE-LINE patch: its static dispatcher whfast_acceleration() forwards to
     grav_b200_shim_whfast_acceleration().  The patched text lives only in a temporary directory.
   * gravity-simulator_b200/csrc/grav_sim_integrators.c (device-resident leapfrog and WHFast time loops) plus a
-    three-line hook at the top of the reference's leapfrog() (src/integrator.c) and whfast(): the hook runs the
+    three-line hook at the top of the reference's leapfrog(), euler(), euler_cromer(), rk4() (src/integrator.c) and
+    whfast(): the hook runs the
     resident loop and returns, or declines (GRAV_B200_RESIDENT=0) and lets the reference's own loop run.
   * the same kind of hook at the top of compute_energy() (src/utils.c) and compute_energy_python()
     (src/python_interface.c): the O(N^2) potential sum runs on the GPU for N >= 1024.
@@ -70,8 +71,9 @@ def main():
             "    return grav_b200_shim_whfast_acceleration(a, system, jacobi_x, eta, acceleration_param);\n")
     patched = src[:m.end()] + hook + src[m.end():]
     patched = resident_hook(patched, r"WIN32DLL_API ErrorStatus whfast\(\s*System \*system,[^)]*\)\s*\{", "grav_b200_shim_whfast")
-    integ = resident_hook((REF / "src" / "integrator.c").read_text(),
-                          r"IN_FILE ErrorStatus leapfrog\(\s*System \*system,[^)]*\)\s*\{", "grav_b200_shim_leapfrog")
+    integ = (REF / "src" / "integrator.c").read_text()
+    for fn in ("leapfrog", "euler", "euler_cromer", "rk4"):
+        integ = resident_hook(integ, r"IN_FILE ErrorStatus " + fn + r"\(\s*System \*system,[^)]*\)\s*\{", "grav_b200_shim_" + fn)
     utils = simple_hook((REF / "src" / "utils.c").read_text(),
                         r"WIN32DLL_API double compute_energy\(const System \*restrict system\)\s*\{",
                         "    extern int grav_b200_shim_compute_energy(double *, const System *);\n"

@@ -276,3 +276,58 @@ def test_dropin_energy_hooks(ics, reference):
     assert abs(out[0] - e_ref) <= 1e-12 * abs(e_ref)
     e2 = reference.energy(x, 0.5 * v, m, G)
     assert abs(out[1] - e2) <= 1e-12 * abs(e2)
+
+
+# ---- Euler / Euler-Cromer / RK4 resident loops (src/integrator.c:281-892) ------------------------------------------
+@pytest.mark.parametrize("integrator", ["euler", "euler_cromer", "rk4"])
+def test_dropin_resident_fixed_step_integrators(ics, tmp_path, integrator):
+    """Barnes-Hut accelerations are bit-identical to the reference's and the update kernels use its operation order,
+    so whole runs (CSV snapshots included) are identical; with the direct sum they agree to rounding."""
+    from oracle.bind import launch_simulation
+    dropin, ref = _dropin()
+    x, v, m, G = ics.two_plummer(350, seed=12)
+    dt, steps = 2e-3, 9
+    outs = {}
+    for name, lib in (("ref", ref), ("dropin", dropin)):
+        d = tmp_path / name
+        d.mkdir()
+        kw = dict(tf=dt * steps - 0.4 * dt, integrator=integrator, dt=dt, method="barnes_hut", opening_angle=0.6, softening_length=0.01,
+                  full=True, output_dir=str(d) + "/", output_interval=3.5 * dt)
+        outs[name] = (launch_simulation(lib, x, v, m, G, **kw), _read_snapshots(d))
+    (fr, sr), (fd, sd) = outs["ref"], outs["dropin"]
+    assert len(sr) >= 3 and sr == sd
+    assert np.array_equal(fd["x"], fr["x"]) and np.array_equal(fd["v"], fr["v"])
+    # direct sum: same run to rounding
+    kw = dict(tf=dt * steps, integrator=integrator, dt=dt, method="pairwise", softening_length=0.01)
+    xr, vr = launch_simulation(ref, x, v, m, G, **kw)
+    xd, vd = launch_simulation(dropin, x, v, m, G, **kw)
+    assert max_rel_err(xd, xr) <= 1e-12 and max_rel_err(vd, vr) <= 1e-10
+
+
+def test_resident_rk4_massless_belt(gb, reference, ics):
+    """SURVEY section 8d, config 3 variant: RK4 with the massless method on the resident state vs the same loop on the host
+    around the reference's acceleration()."""
+    x, v, m, G = ics.asteroid_belt(3000, 15)
+    dt, steps = 0.1, 5
+    acc = lambda xx: reference.acceleration(xx, m, G, "massless", 0.0)
+    xr, vr = x.copy(), v.copy()
+    xc, vc = np.zeros_like(x), np.zeros_like(v)
+    for _ in range(steps):                     # src/integrator.c:742-850
+        x0, v0 = xr.copy(), vr.copy()
+        vk1 = acc(xr); xk1 = vr.copy()
+        xr = x0 + 0.5 * xk1 * dt; vr = v0 + 0.5 * vk1 * dt
+        vk2 = acc(xr); xk2 = vr.copy()
+        xr = x0 + 0.5 * xk2 * dt; vr = v0 + 0.5 * vk2 * dt
+        vk3 = acc(xr); xk3 = vr.copy()
+        xr = x0 + xk3 * dt; vr = v0 + vk3 * dt
+        vk4 = acc(xr); xk4 = vr.copy()
+        vc += (vk1 + 2 * vk2 + 2 * vk3 + vk4) * dt / 6.0
+        xc += (xk1 + 2 * xk2 + 2 * xk3 + xk4) * dt / 6.0
+        vr = v0 + vc; xr = x0 + xc
+        vc += v0 - vr; xc += x0 - xr
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.fixed_begin("rk4", "massless", 0.0)
+        c.fixed_steps(dt, steps)
+        xg, vg = c.positions(), c.velocities()
+    assert max_rel_err(xg, xr) <= 1e-13 and max_rel_err(vg, vr) <= 1e-11

@@ -24,6 +24,23 @@ for n in (9, 300, 1111, 5000):
         c.leapfrog_steps(1e-3, 2)
         c.energy(); c.positions(); c.velocities()
         c.leapfrog_end()
+# resident integrators: WHFast (graph pairs, small-n sort, removal replay), Euler / Euler-Cromer / RK4, one-shot energy
+for k, grazers, steps in ((600, 0, 7), (1500, 20, 6)):
+    x, v, m, G = ics.asteroid_belt(k, 3, grazers=grazers)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.whfast_begin(180.0, "massless", 0.0, True)
+        c.whfast_steps(180.0, steps)
+        c.whfast_state(snapshot=True); c.whfast_state(snapshot=False)
+        c.whfast_end()
+x, v, m, G = ics.two_plummer(700, seed=2)
+for integ in ("euler", "euler_cromer", "rk4"):
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.fixed_begin(integ, "barnes_hut", 0.01, 0.5, 1)
+        c.fixed_steps(1e-3, 2)
+        c.positions(); c.velocities()
+gb.compute_energy(x, v, m, G)
 x, v, m, G = ics.plummer(40000, 1)
 gb.acceleration(x, m, G, "pairwise", 0.01)      # fast kernel + fix-up + special-tile kernel
 gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)

@@ -33,6 +33,7 @@ namespace gb {
 
 constexpr int MAX_LEVEL = 21;
 constexpr int WALK_BLOCK = 128;
+constexpr int WALK_CHUNK = 2048;    // multi-GPU: granularity of the interleaved target partition (16 CTAs)
 // Tuning knobs kept for A/B builds (measured at N=2^20 Plummer, reference mode):
 //   WALK_VARIANT 0  next node's record prefetched into registers before the arithmetic        39.3 ms  <- default
 //   WALK_VARIANT 1  prefetch.global.L1 + reload at loop top (12 fewer live registers)          41.9 ms
@@ -53,6 +54,7 @@ struct WalkArgs {
     const double4 *psorted;    // particle records in sorted order
     const int *tord;           // optional: thread q handles sorted position tord[q] (walk-key grouping), else q
     int p_lo, p_hi;            // sorted positions (or slots of tord) handled by this launch
+    int chunk, rank, world;    // world > 1: the launch covers chunks rank, rank + world, ... of `chunk` consecutive slots
     double G, eps2, theta2;
     double cell2[MAX_LEVEL + 2];   // (box_length / (2 << level))^2 per child level
     double *acc;               // AoS [3n] by particle id
@@ -94,7 +96,13 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
     __shared__ double s_cell2[MAX_LEVEL + 2];
     if (threadIdx.x < MAX_LEVEL + 2) s_cell2[threadIdx.x] = a.cell2[threadIdx.x];
     __syncthreads();
-    const int q = a.p_lo + blockIdx.x * WALK_BLOCK + threadIdx.x;
+    int q = a.p_lo + blockIdx.x * WALK_BLOCK + threadIdx.x;
+    if (a.world > 1) {
+        // interleaved chunks: walk cost varies smoothly along the Morton curve (dense centre vs halo), so every rank
+        // gets a sample of all regions instead of one contiguous stretch
+        const int t = blockIdx.x * WALK_BLOCK + threadIdx.x;
+        q = ((t / a.chunk) * a.world + a.rank) * a.chunk + t % a.chunk;
+    }
     if (q >= a.p_hi) return;
     const int p = a.tord ? a.tord[q] : q;
     const int idx = a.perm[p];
@@ -212,9 +220,11 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
     a.K = t.keys.as<long long>();
     a.perm = t.perm.as<int>();
     a.psorted = t.posm_sorted.as<double4>();
-    // ranks share the walk by sorted position (Morton-contiguous), not by particle id
-    a.p_lo = (int)(((long long)c->rank * c->n) / c->world);
-    a.p_hi = (int)(((long long)(c->rank + 1) * c->n) / c->world);
+    // ranks share the walk by sorted position, not by particle id: interleaved chunks of WALK_CHUNK positions
+    // (contiguous equal-count slices left the rank holding a Plummer sphere's centre 12 % behind at N = 2^24)
+    a.p_lo = 0;
+    a.p_hi = c->n;
+    a.chunk = WALK_CHUNK; a.rank = c->rank; a.world = c->world;
     a.G = c->G;
     a.eps2 = eps * eps;
     a.theta2 = theta * theta;
@@ -241,7 +251,12 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
         a.tord = pos;
     }
     if (c->world > 1) GB_CUDA(cudaMemsetAsync(a.acc, 0, sizeof(double) * 3 * (size_t)c->n, c->stream));
-    const int npos = a.p_hi - a.p_lo;
+    int npos = a.p_hi - a.p_lo;
+    if (c->world > 1) {   // slots of this rank: its share of the WALK_CHUNK-sized chunks (the last one may be partial)
+        const int chunks = (c->n + WALK_CHUNK - 1) / WALK_CHUNK;
+        const int mine = chunks > c->rank ? (chunks - c->rank + c->world - 1) / c->world : 0;
+        npos = mine * WALK_CHUNK;
+    }
     if (npos > 0) {
         const int blocks = (npos + WALK_BLOCK - 1) / WALK_BLOCK;
         if (c->bh_mode == GRAV_B200_BH_FIXED) walk_kernel<true><<<blocks, WALK_BLOCK, 0, c->stream>>>(a);

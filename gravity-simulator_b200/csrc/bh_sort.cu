@@ -290,6 +290,185 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const long l
     }
 }
 
+
+// ---- large n: one kernel per pass ("onesweep": chained scan with decoupled look-back) ---------------------------------
+// ncu on the three-kernel pass at N = 2^24 (profiles/r1_sort_n16m.txt): both sort kernels sit on one saturated pipe
+// (sm__throughput 91 % / 72 % with 9-11 % issue activity) -- MATCH.ANY retires about one warp instruction per 64 cycles
+// per SM, and a pass executed three of them per 32 pairs (histogram kernel, counting and placement in the scatter
+// kernel).  This version needs ONE: the peer mask of every round is kept in a register, the warp-local rank of a pair is
+// fixed while counting (the leader lane hands out the running count of its digit), and the per-tile digit counts are
+// published for the tiles behind it instead of being computed by a separate histogram kernel + scan:
+//   upfront   sort_global_hist_kernel: digit totals of all 8 passes from one read of the keys (they do not depend on the
+//             order of the pairs) -> first output slot of every digit value
+//   per pass  tile id from an atomic ticket (so every tile only waits for tiles that already started), counts, then
+//             thread d publishes (count | AGGREGATE) for digit d, walks back over earlier tiles adding their words until
+//             it meets an inclusive PREFIX, publishes its own (prefix | PREFIX), and the tile is scattered as before.
+// A status word carries flag and value together (2 + 30 bits), so no fence is needed.
+constexpr unsigned OSW_FLAG_AGG = 1u << 30, OSW_FLAG_PREFIX = 2u << 30, OSW_VALUE_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_global_hist_kernel(const long long *__restrict__ keys, int n, int *__restrict__ ghist)
+{
+    __shared__ int h[8][SORT_RADIX];
+    for (int i = threadIdx.x; i < 8 * SORT_RADIX; i += SORT_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * SORT_THREADS; base < n; base += gridDim.x * SORT_THREADS) {
+        const int i = base + threadIdx.x;
+        const bool valid = i < n;
+        const unsigned long long k = valid ? (unsigned long long)keys[i] : 0ull;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            const int d = (int)(k >> (8 * p)) & (SORT_RADIX - 1);
+            // the high digits of sorted-ish keys are equal across the warp: one add instead of a 32-way conflict
+            const int d0 = __shfl_sync(0xffffffffu, d, __ffs(act) - 1);
+            if (__all_sync(0xffffffffu, !valid || d == d0)) {
+                if (lane == __ffs(act) - 1) atomicAdd(&h[p][d0], __popc(act));
+            } else if (valid) {
+                atomicAdd(&h[p][d], 1);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * SORT_RADIX; i += SORT_THREADS) {
+        const int c = (&h[0][0])[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+__device__ __forceinline__ unsigned ld_status(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned *p, unsigned v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int ROUNDS>
+__global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_kernel(const long long *__restrict__ keys_in,
+                                                                     const int *__restrict__ vals_in, int n, int shift,
+                                                                     const int *__restrict__ ghist_pass, unsigned *__restrict__ status,
+                                                                     int *__restrict__ ticket, long long *__restrict__ keys_out,
+                                                                     int *__restrict__ vals_out)
+{
+    constexpr int TILE = SORT_THREADS * ROUNDS;
+    constexpr int WCHUNK = 32 * ROUNDS;
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    long long *skeys = reinterpret_cast<long long *>(sort_smem);
+    int *svals = reinterpret_cast<int *>(sort_smem + (size_t)TILE * sizeof(long long));
+    __shared__ int wcnt[SORT_WARPS][SORT_RADIX];
+    __shared__ int gbase[SORT_RADIX];
+    __shared__ int wsum[SORT_WARPS], wsum2[SORT_WARPS];
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);
+    for (int d = lane; d < SORT_RADIX; d += 32) wcnt[warp][d] = 0;
+    __syncthreads();
+    const int tile = s_tile;
+    const int base = tile * TILE;
+    const int tile_n = min(TILE, n - base);
+
+    // (1) load this warp's sub-chunk in order, count digits, fix the warp-local rank of every pair
+    long long k[ROUNDS];
+    int v[ROUNDS];
+    unsigned short rk[ROUNDS];
+    const int wbase = warp * WCHUNK;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        k[r] = valid ? keys_in[base + li] : 0;
+        v[r] = valid ? vals_in[base + li] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
+        const unsigned same = __match_any_sync(0xffffffffu, d);
+        const int leader = 31 - __clz(same);
+        int prev = 0;
+        if (valid && lane == leader) {
+            prev = wcnt[warp][d];
+            wcnt[warp][d] = prev + __popc(same);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rk[r] = (unsigned short)(prev + __popc(same & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // (2) thread d owns digit d: local slots, publish / look back, global base
+    {
+        const int d = tid;
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            const int t = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += t;
+        }
+        unsigned *my = status + (size_t)tile * SORT_RADIX + d;
+        st_status(my, (unsigned)run | (tile == 0 ? OSW_FLAG_PREFIX : OSW_FLAG_AGG));
+        // exclusive scans over the digits: this tile's counts (local slots) and the global totals (first slot per digit)
+        const int tot = ghist_pass[d];
+        int inc = run, ginc = tot;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, s2);
+            const int g = __shfl_up_sync(0xffffffffu, ginc, s2);
+            if (lane >= s2) { inc += t; ginc += g; }
+        }
+        if (lane == 31) { wsum[warp] = inc; wsum2[warp] = ginc; }
+        __syncthreads();
+        int woff = 0, goff = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            woff += (w < warp) ? wsum[w] : 0;
+            goff += (w < warp) ? wsum2[w] : 0;
+        }
+        const int dstart = woff + inc - run;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) wcnt[w][d] += dstart;
+        int excl = 0;
+        for (int t = tile - 1; t >= 0; t--) {
+            const unsigned *p = status + (size_t)t * SORT_RADIX + d;
+            unsigned sv;
+            do { sv = ld_status(p); } while ((sv >> 30) == 0u);
+            excl += (int)(sv & OSW_VALUE_MASK);
+            if (sv & OSW_FLAG_PREFIX) break;
+        }
+        if (tile > 0) st_status(my, (unsigned)(excl + run) | OSW_FLAG_PREFIX);
+        gbase[d] = (goff + ginc - tot) + excl - dstart;
+    }
+    __syncthreads();
+
+    // (3) place every pair at its slot of the digit-sorted tile
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        if (li < tile_n) {
+            const int slot = wcnt[warp][digit_of(k[r], shift)] + rk[r];
+            skeys[slot] = k[r];
+            svals[slot] = v[r];
+        }
+    }
+    __syncthreads();
+
+    // (4) stream the sorted tile out
+    for (int i = tid; i < tile_n; i += SORT_THREADS) {
+        const long long kk = skeys[i];
+        const int pos = gbase[digit_of(kk, shift)] + i;
+        keys_out[pos] = kk;
+        vals_out[pos] = svals[i];
+    }
+}
+
 // One stable pass on an 8-bit digit of arbitrary (key, value) arrays; scratch: t.hist / t.scan_tmp.
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift)
 {
@@ -326,6 +505,41 @@ int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long
     return GRAV_B200_OK;
 }
 
+// All 8 passes of a large sort with the one-kernel-per-pass scheme above; ka/pa hold the result (even pass count).
+static int onesweep_sort(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
+{
+    DevTree &t = c->tree;
+    constexpr int TILE = SORT_THREADS * SORT_ROUNDS;
+    constexpr size_t SMEM = (size_t)TILE * (sizeof(long long) + sizeof(int));
+    static bool attr_set = false;
+    if (!attr_set) {
+        GB_CUDA(cudaFuncSetAttribute(sort_onesweep_kernel<SORT_ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_set = true;
+    }
+    const int num_tiles = (n + TILE - 1) / TILE;
+    // scratch layout (ints): [0, 2048) digit totals of the 8 passes, [2048, 2056) tickets, then 8 x num_tiles x 256 status words
+    const size_t head = 8 * SORT_RADIX + 8;
+    const size_t words = head + (size_t)8 * num_tiles * SORT_RADIX;
+    GB_TRY(t.hist.reserve(sizeof(int) * words));
+    int *scratch = t.hist.as<int>();
+    GB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * words, c->stream));
+    int gblocks = (n + SORT_THREADS * 8 - 1) / (SORT_THREADS * 8);
+    if (gblocks > c->sm_count * 8) gblocks = c->sm_count * 8;
+    sort_global_hist_kernel<<<gblocks, SORT_THREADS, 0, c->stream>>>(ka, n, scratch);
+    GB_LAUNCH_CHECK();
+    count_launch();
+    for (int pass = 0; pass < 8; pass++) {
+        unsigned *status = reinterpret_cast<unsigned *>(scratch + head) + (size_t)pass * num_tiles * SORT_RADIX;
+        sort_onesweep_kernel<SORT_ROUNDS><<<num_tiles, SORT_THREADS, SMEM, c->stream>>>(ka, pa, n, pass * SORT_BITS, scratch + pass * SORT_RADIX,
+                                                                                      status, scratch + 8 * SORT_RADIX + pass, kb, pb);
+        GB_LAUNCH_CHECK();
+        count_launch();
+        long long *tk = ka; ka = kb; kb = tk;
+        int *tp = pa; pa = pb; pb = tp;
+    }
+    return GRAV_B200_OK;
+}
+
 // keys/perm sorted in place (8 passes ping-pong through keys_tmp/perm_tmp)
 int radix_sort_pairs(grav_b200_ctx *c)
 {
@@ -335,6 +549,8 @@ int radix_sort_pairs(grav_b200_ctx *c)
     GB_TRY(t.perm_tmp.reserve(sizeof(int) * (size_t)n));
     long long *ka = t.keys.as<long long>(), *kb = t.keys_tmp.as<long long>();
     int *pa = t.perm.as<int>(), *pb = t.perm_tmp.as<int>();
+    static const bool three_kernel = getenv("GRAV_B200_SORT_THREE_KERNEL") && atoi(getenv("GRAV_B200_SORT_THREE_KERNEL")) != 0;
+    if (n > SORT_SMALL_MAX_N && !three_kernel) return onesweep_sort(c, ka, pa, kb, pb, n);
     for (int pass = 0; pass < 8; pass++) {
         GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * SORT_BITS));
         long long *tk = ka; ka = kb; kb = tk;

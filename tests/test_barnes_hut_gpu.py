@@ -62,7 +62,8 @@ def test_morton_keys_stage(gb, oracle, ics):
     assert (k[i] >> widest) & 0x1249249249249249 == 0
 
 
-@pytest.mark.parametrize("n,leaf", [(1 << 15, 1), (50000, 2), (1 << 17, 1), (100003, 8)])
+@pytest.mark.parametrize("n,leaf", [(1 << 15, 1), (50000, 2), (1 << 17, 1), (100003, 8),
+                                    (131073, 1), (300007, 1), (1 << 19, 3)])      # > 131072: one-kernel-per-pass sort
 def test_tree_vs_oracle_large(gb, oracle, ics, n, leaf):
     for name, (x, v, m, G) in {"plummer": ics.plummer(n, n), "uniform": ics.uniform_cube(n, n + 1)}.items():
         m = m * np.random.default_rng(n).uniform(0.5, 1.5, n)

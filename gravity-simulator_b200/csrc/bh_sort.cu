@@ -506,14 +506,15 @@ int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long
 }
 
 // All 8 passes of a large sort with the one-kernel-per-pass scheme above; ka/pa hold the result (even pass count).
-static int onesweep_sort(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
+template <int ROUNDS>
+static int onesweep_sort_t(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
 {
     DevTree &t = c->tree;
-    constexpr int TILE = SORT_THREADS * SORT_ROUNDS;
+    constexpr int TILE = SORT_THREADS * ROUNDS;
     constexpr size_t SMEM = (size_t)TILE * (sizeof(long long) + sizeof(int));
     static bool attr_set = false;
     if (!attr_set) {
-        GB_CUDA(cudaFuncSetAttribute(sort_onesweep_kernel<SORT_ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        GB_CUDA(cudaFuncSetAttribute(sort_onesweep_kernel<ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
     const int num_tiles = (n + TILE - 1) / TILE;
@@ -530,14 +531,21 @@ static int onesweep_sort(grav_b200_ctx *c, long long *ka, int *pa, long long *kb
     count_launch();
     for (int pass = 0; pass < 8; pass++) {
         unsigned *status = reinterpret_cast<unsigned *>(scratch + head) + (size_t)pass * num_tiles * SORT_RADIX;
-        sort_onesweep_kernel<SORT_ROUNDS><<<num_tiles, SORT_THREADS, SMEM, c->stream>>>(ka, pa, n, pass * SORT_BITS, scratch + pass * SORT_RADIX,
-                                                                                      status, scratch + 8 * SORT_RADIX + pass, kb, pb);
+        sort_onesweep_kernel<ROUNDS><<<num_tiles, SORT_THREADS, SMEM, c->stream>>>(ka, pa, n, pass * SORT_BITS, scratch + pass * SORT_RADIX,
+                                                                                 status, scratch + 8 * SORT_RADIX + pass, kb, pb);
         GB_LAUNCH_CHECK();
         count_launch();
         long long *tk = ka; ka = kb; kb = tk;
         int *tp = pa; pa = pb; pb = tp;
     }
     return GRAV_B200_OK;
+}
+static int onesweep_sort(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
+{
+    static const int rounds = getenv("GRAV_B200_SORT_ROUNDS") ? atoi(getenv("GRAV_B200_SORT_ROUNDS")) : SORT_ROUNDS;
+    if (rounds == 8) return onesweep_sort_t<8>(c, ka, pa, kb, pb, n);
+    if (rounds == 12) return onesweep_sort_t<12>(c, ka, pa, kb, pb, n);
+    return onesweep_sort_t<SORT_ROUNDS>(c, ka, pa, kb, pb, n);
 }
 
 // keys/perm sorted in place (8 passes ping-pong through keys_tmp/perm_tmp)

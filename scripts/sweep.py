@@ -66,13 +66,16 @@ def timed(n, kind, method, reps, **kw):
     return best, stages
 
 
+# optional subsets (an 8-GPU box is charged 8x): SWEEP_DS_EXP="16,20" SWEEP_BH_EXP="20,24"
+DS_EXP = [int(t) for t in os.environ["SWEEP_DS_EXP"].split(",") if t] if "SWEEP_DS_EXP" in os.environ else list(range(16, 21))
+BH_EXP = [int(t) for t in os.environ["SWEEP_BH_EXP"].split(",") if t] if "SWEEP_BH_EXP" in os.environ else list(range(20, 25))
 for kind in ("plummer", "uniform"):
-    for e in range(16, 21):
+    for e in DS_EXP:
         n = 1 << e
         ms, st = timed(n, kind, "pairwise", 3 if e >= 19 else 6, softening_length=0.01)
         rows.append({"path": "direct_sum", "ic": kind, "n": n, "gpus": world, "ms": ms, "G_interactions_per_s": n * (n - 1.0) / ms / 1e6,
                      "allgather_ms": st[0]})
-    for e in range(20, 25):
+    for e in BH_EXP:
         n = 1 << e
         ms, st = timed(n, kind, "barnes_hut", 2, softening_length=0.01, opening_angle=0.5, max_num_particles_per_leaf=1)
         rows.append({"path": "barnes_hut", "ic": kind, "n": n, "gpus": world, "ms": ms,

@@ -244,42 +244,57 @@ __global__ void __launch_bounds__(DS_BLOCK) direct_sum_special_kernel(const DSAr
     }
 }
 
-// Adds the partial sums of every target block that was split over several CTAs, in CTA order.
+// Adds the partial sums of every target block that was split over several CTAs, in CTA order.  One CTA per 256
+// targets (grid = NB x TI); the CTA range of the block and the slot each of those CTAs used are worked out once per
+// CTA (the 64-bit divisions of unit_begin() per target and contributor made the first version of this kernel cost
+// 16 % of a force evaluation at N = 16384).
+constexpr int DS_FIXUP_MAX_CONTRIB = 1024;
 template <int TI>
 __global__ void __launch_bounds__(DS_BLOCK) direct_sum_fixup_kernel(const DSArgs p, int C)
 {
     constexpr int IB = DS_BLOCK * TI;
+    __shared__ int s_range[2];
+    __shared__ signed char s_slot[DS_FIXUP_MAX_CONTRIB];     // 0 / 1: partial slot of contributor c_lo + k, -1: none
     const int ib = blockIdx.x;
     const long long U = (long long)p.NB * p.NT;
-    const long long ua = (long long)ib * p.NT, ub = ua + p.NT - 1;
-    // owner(u) = largest c with unit_begin(c) <= u
-    auto owner = [&](long long u) {
-        int lo = 0, hi = C - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (unit_begin(mid, U, C) <= u) lo = mid; else hi = mid - 1;
-        }
-        return lo;
-    };
-    const int c_lo = owner(ua), c_hi = owner(ub);
-    if (c_lo == c_hi) return;   // one CTA had the whole block and wrote acc itself
-    for (int li = threadIdx.x; li < IB; li += DS_BLOCK) {
-        const int i = p.i_lo + ib * IB + li;
-        if (i >= p.i_hi) continue;
-        double sx = 0.0, sy = 0.0, sz = 0.0;
-        for (int c = c_lo; c <= c_hi; c++) {
-            const long long b = unit_begin(c, U, C), e = unit_begin(c + 1, U, C);
-            if (b >= e) continue;
-            const int slot = ((int)(b / p.NT) == ib) ? 0 : 1;
-            const double *src = p.partials + ((size_t)c * 2 + slot) * 3 * IB;
-            sx += src[0 * IB + li];
-            sy += src[1 * IB + li];
-            sz += src[2 * IB + li];
-        }
-        p.acc[3 * (size_t)i + 0] = p.G * sx;
-        p.acc[3 * (size_t)i + 1] = p.G * sy;
-        p.acc[3 * (size_t)i + 2] = p.G * sz;
+    if (threadIdx.x == 0) {
+        const long long ua = (long long)ib * p.NT, ub = ua + p.NT - 1;
+        // owner(u) = largest c with unit_begin(c) <= u
+        auto owner = [&](long long u) {
+            int lo = 0, hi = C - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (unit_begin(mid, U, C) <= u) lo = mid; else hi = mid - 1;
+            }
+            return lo;
+        };
+        s_range[0] = owner(ua);
+        s_range[1] = owner(ub);
     }
+    __syncthreads();
+    const int c_lo = s_range[0], c_hi = s_range[1];
+    if (c_lo == c_hi) return;   // one CTA had the whole block and wrote acc itself
+    for (int k = threadIdx.x; k <= c_hi - c_lo; k += DS_BLOCK) {
+        const int c = c_lo + k;
+        const long long b = unit_begin(c, U, C), e = unit_begin(c + 1, U, C);
+        s_slot[k] = (b >= e) ? -1 : (((int)(b / p.NT) == ib) ? 0 : 1);
+    }
+    __syncthreads();
+    const int li = blockIdx.y * DS_BLOCK + threadIdx.x;
+    const int i = p.i_lo + ib * IB + li;
+    if (i >= p.i_hi) return;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int k = 0; k <= c_hi - c_lo; k++) {
+        const int slot = s_slot[k];
+        if (slot < 0) continue;
+        const double *src = p.partials + ((size_t)(c_lo + k) * 2 + slot) * 3 * IB;
+        sx += src[0 * IB + li];
+        sy += src[1 * IB + li];
+        sz += src[2 * IB + li];
+    }
+    p.acc[3 * (size_t)i + 0] = p.G * sx;
+    p.acc[3 * (size_t)i + 1] = p.G * sy;
+    p.acc[3 * (size_t)i + 2] = p.G * sz;
 }
 
 constexpr int DS_TI = 4;
@@ -303,6 +318,7 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
     const bool all_checked = MASSLESS || a.NT <= checked_max_tiles;
     const long long U = (long long)a.NB * a.NT;
     long long grid = (long long)c->sm_count * 2;
+    if (grid > DS_FIXUP_MAX_CONTRIB) grid = DS_FIXUP_MAX_CONTRIB;   // the fix-up kernel's per-block contributor table
     if (grid > U) grid = U;
     GB_TRY(c->partials.reserve((size_t)grid * 2 * 3 * IB * sizeof(double)));
     a.partials = c->partials.as<double>();
@@ -314,7 +330,7 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
     bool split = false;
     for (long long k = 1; k < grid && !split; k++) split = (unit_begin(k, U, grid) % a.NT) != 0;
     if (split) {
-        direct_sum_fixup_kernel<TI><<<a.NB, DS_BLOCK, 0, c->stream>>>(a, (int)grid);
+        direct_sum_fixup_kernel<TI><<<dim3(a.NB, TI), DS_BLOCK, 0, c->stream>>>(a, (int)grid);
         GB_LAUNCH_CHECK();
         count_launch();
     }

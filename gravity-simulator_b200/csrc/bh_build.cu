@@ -8,8 +8,8 @@
 //
 //   discovery   breadth-first.  The root is always expanded.  The children of an expanded node of level
 //               l-1 are the maximal runs of equal (key >> 3(21-l)) in its sorted range; a child is
-//               expanded iff it holds more than max_leaf particles and l < 21.  One thread per expanded
-//               node finds the (at most 8) run boundaries by binary search; the next level's records are
+//               expanded iff it holds more than max_leaf particles and l < 21.  Eight lanes per expanded
+//               node find the octant boundaries by binary search; the next level's records are
 //               placed with a prefix sum, so record order is deterministic (by start position).
 //   numbering   the reference serves expanded nodes in (start position, level) order and gives each all of
 //               its children at once, so   first_child(u) = 1 + P[s_u] + same_start(u)   where P is the
@@ -51,50 +51,48 @@ __global__ void root_init_kernel(ExpRec *rec, int n)
     rec[0] = r;
 }
 
-// first position q in (p, e) whose level prefix differs from that of p (keys are sorted => it is larger)
-__device__ __forceinline__ int run_end(const long long *__restrict__ K, int p, int e, int shift)
-{
-    const long long v = K[p] >> shift;
-    if (e - p <= 16) {
-        int q = p + 1;
-        while (q < e && (K[q] >> shift) == v) q++;
-        return q;
-    }
-    int lo = p + 1, hi = e;   // answer in [lo, hi]
-    while (lo < hi) {
-        const int mid = lo + ((hi - lo) >> 1);
-        if ((K[mid] >> shift) == v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
+// Eight lanes per expanded node, one per octant: lane o finds the first position of the node's range whose level-l
+// digit is >= o (all keys of the range share the higher bits), so the eight binary searches -- chains of dependent L2
+// loads -- run side by side instead of one after the other (16 x 25 us -> 16 x 6 us of build time at N = 60000).  The
+// non-empty octants, in order, are the children.
 __global__ void __launch_bounds__(128) expand_kernel(ExpRec *__restrict__ rec, int begin, int count,
                                                     const long long *__restrict__ K, int max_leaf,
                                                     int *__restrict__ W, int *__restrict__ nexp)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = gt >> 3, o = gt & 7;
     if (t >= count) {
-        if (t == count) nexp[t] = 0;   // sentinel so the scan also yields the total
-        return;
+        if (t == count && o == 0) nexp[t] = 0;   // sentinel so the scan also yields the total
+        return;                                   // count * 8 is a multiple of 8: whole octets leave together
     }
-    ExpRec r = rec[begin + t];
-    const int s = r.b[0], e = r.b[1];
-    const int l = r.level + 1, shift = 3 * (MAX_LEVEL - l);
-    int nch = 0, grow = 0;
-    int p = s;
-    while (p < e) {
-        const int q = run_end(K, p, e, shift);
-        r.b[nch] = p;
-        nch++;
-        if (q - p > max_leaf && l < MAX_LEVEL) grow++;
-        p = q;
+    ExpRec *r = rec + begin + t;
+    const int s = r->b[0], e = r->b[1];
+    const int l = r->level + 1, shift = 3 * (MAX_LEVEL - l);
+    // lower bound of digit o in [s, e)
+    int lo = s, hi = e;
+    if (o > 0) {
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if ((int)((K[mid] >> shift) & 7) < o) lo = mid + 1; else hi = mid;
+        }
     }
-    r.b[nch] = e;
-    for (int k = nch + 1; k < 9; k++) r.b[k] = e;
-    r.nch = nch;
-    rec[begin + t] = r;
-    nexp[t] = grow;
-    atomicAdd(&W[s], nch);
+    const int lane = threadIdx.x & 31, g0 = lane & ~7;
+    const unsigned gmask = 0xffu << g0;
+    const int up = __shfl_down_sync(gmask, lo, 1, 8);
+    const int end = (o == 7) ? e : up;
+    const bool nonempty = end > lo;
+    const bool grows = nonempty && (end - lo > max_leaf) && l < MAX_LEVEL;
+    const unsigned ne_mask = (__ballot_sync(gmask, nonempty) >> g0) & 0xffu;
+    const unsigned gr_mask = (__ballot_sync(gmask, grows) >> g0) & 0xffu;
+    const int nch = __popc(ne_mask);
+    if (nonempty) r->b[__popc(ne_mask & ((1u << o) - 1u))] = lo;
+    // slots nch .. 8 hold the end of the range (lane o takes slot nch + o; nch >= 1, so 8 lanes cover them)
+    if (nch + o <= 8) r->b[nch + o] = e;
+    if (o == 0) {
+        r->nch = nch;
+        nexp[t] = __popc(gr_mask);
+        atomicAdd(&W[s], nch);
+    }
 }
 
 __global__ void __launch_bounds__(128) emit_kernel(ExpRec *__restrict__ rec, int begin, int count, int next_begin,
@@ -297,7 +295,7 @@ int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double bo
         const int begin = level_off[l], count = level_off[l + 1] - begin;
         GB_TRY(t.counters.reserve(sizeof(int) * ((size_t)count + 1)));
         int *nexp = t.counters.as<int>();
-        expand_kernel<<<(count + 1 + 127) / 128, 128, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, K, max_leaf,
+        expand_kernel<<<(8 * (count + 1) + 127) / 128, 128, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, K, max_leaf,
                                                                      t.wsum.as<int>(), nexp);
         GB_LAUNCH_CHECK();
         count_launch();

@@ -469,6 +469,153 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_kernel(const long 
     }
 }
 
+// ---- small n (<= 128 tiles of 1024 pairs): one kernel per pass, every CTA reads every tile's digit counts -----------
+// All CTAs of the grid are resident at once (<= 128 CTAs of 256 threads), so a tile can simply wait until the digit
+// counts of ALL tiles have been published: status[tile][d] = count | VALID.  Thread d then knows the pairs with digit d
+// in earlier tiles and in total; a block scan over the totals gives the digit's first output slot.  One launch per pass
+// (the two-launch version above needs the histogram kernel to finish first); the waits are batched so the ~100 loads
+// per thread overlap.
+constexpr unsigned SMALL_VALID = 0x80000000u;
+
+template <int ROUNDS>
+__global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const long long *__restrict__ keys_in,
+                                                                       const int *__restrict__ vals_in, int n, int shift,
+                                                                       int num_tiles, unsigned *__restrict__ status,
+                                                                       long long *__restrict__ keys_out, int *__restrict__ vals_out)
+{
+    constexpr int TILE = SORT_THREADS * ROUNDS;
+    constexpr int WCHUNK = 32 * ROUNDS;
+    __shared__ long long skeys[TILE];
+    __shared__ int svals[TILE];
+    __shared__ int wcnt[SORT_WARPS][SORT_RADIX];
+    __shared__ int gbase[SORT_RADIX];
+    __shared__ int wsum[SORT_WARPS], wsum2[SORT_WARPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int tile = blockIdx.x;
+    const int base = tile * TILE;
+    const int tile_n = min(TILE, n - base);
+    for (int d = lane; d < SORT_RADIX; d += 32) wcnt[warp][d] = 0;
+    __syncwarp();
+
+    long long k[ROUNDS];
+    int v[ROUNDS];
+    unsigned short rk[ROUNDS];
+    const int wbase = warp * WCHUNK;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        k[r] = valid ? keys_in[base + li] : 0;
+        v[r] = valid ? vals_in[base + li] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
+        const unsigned same = __match_any_sync(0xffffffffu, d);
+        const int leader = 31 - __clz(same);
+        int prev = 0;
+        if (valid && lane == leader) {
+            prev = wcnt[warp][d];
+            wcnt[warp][d] = prev + __popc(same);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rk[r] = (unsigned short)(prev + __popc(same & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    {
+        const int d = tid;
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            const int t = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += t;
+        }
+        st_status(status + (size_t)tile * SORT_RADIX + d, (unsigned)run | SMALL_VALID);
+        // every tile's count of digit d: batches of 8 independent loads, then spin only on the stragglers
+        int tot = 0, before = 0;
+        for (int t0 = 0; t0 < num_tiles; t0 += 8) {
+            unsigned w8[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) w8[j] = (t0 + j < num_tiles) ? ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d) : SMALL_VALID;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                unsigned sv = w8[j];
+                while (!(sv & SMALL_VALID)) sv = ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d);
+                const int h = (int)(sv & ~SMALL_VALID);
+                tot += h;
+                if (t0 + j < tile) before += h;
+            }
+        }
+        int inc = run, ginc = tot;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, s2);
+            const int g = __shfl_up_sync(0xffffffffu, ginc, s2);
+            if (lane >= s2) { inc += t; ginc += g; }
+        }
+        if (lane == 31) { wsum[warp] = inc; wsum2[warp] = ginc; }
+        __syncthreads();
+        int woff = 0, goff = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            woff += (w < warp) ? wsum[w] : 0;
+            goff += (w < warp) ? wsum2[w] : 0;
+        }
+        const int dstart = woff + inc - run;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) wcnt[w][d] += dstart;
+        gbase[d] = (goff + ginc - tot) + before - dstart;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        if (li < tile_n) {
+            const int slot = wcnt[warp][digit_of(k[r], shift)] + rk[r];
+            skeys[slot] = k[r];
+            svals[slot] = v[r];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < tile_n; i += SORT_THREADS) {
+        const long long kk = skeys[i];
+        const int pos = gbase[digit_of(kk, shift)] + i;
+        keys_out[pos] = kk;
+        vals_out[pos] = svals[i];
+    }
+}
+
+// All 8 passes of a small sort (n <= SORT_SMALL_MAX_N): one memset + 8 launches; ka/pa hold the result.
+int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
+{
+    DevTree &t = c->tree;
+    constexpr int TILE = SORT_THREADS * SORT_ROUNDS_SMALL;
+    const int num_tiles = (n + TILE - 1) / TILE;
+    const size_t words = (size_t)8 * num_tiles * SORT_RADIX;
+    GB_TRY(t.hist.reserve(sizeof(int) * words));
+    unsigned *status = t.hist.as<unsigned>();
+    GB_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * words, c->stream));
+    for (int pass = 0; pass < 8; pass++) {
+        sort_small_pass_kernel<SORT_ROUNDS_SMALL><<<num_tiles, SORT_THREADS, 0, c->stream>>>(ka, pa, n, pass * SORT_BITS, num_tiles,
+                                                                                            status + (size_t)pass * num_tiles * SORT_RADIX, kb, pb);
+        GB_LAUNCH_CHECK();
+        count_launch();
+        long long *tk = ka; ka = kb; kb = tk;
+        int *tp = pa; pa = pb; pb = tp;
+    }
+    return GRAV_B200_OK;
+}
+
+extern const int sort_small_max_n = SORT_SMALL_MAX_N;
+
 // One stable pass on an 8-bit digit of arbitrary (key, value) arrays; scratch: t.hist / t.scan_tmp.
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift)
 {
@@ -559,6 +706,8 @@ int radix_sort_pairs(grav_b200_ctx *c)
     int *pa = t.perm.as<int>(), *pb = t.perm_tmp.as<int>();
     static const bool three_kernel = getenv("GRAV_B200_SORT_THREE_KERNEL") && atoi(getenv("GRAV_B200_SORT_THREE_KERNEL")) != 0;
     if (n > SORT_SMALL_MAX_N && !three_kernel) return onesweep_sort(c, ka, pa, kb, pb, n);
+    static const bool two_launch = getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH") && atoi(getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH")) != 0;
+    if (n <= SORT_SMALL_MAX_N && !two_launch) return radix_sort_small(c, ka, pa, kb, pb, n);
     for (int pass = 0; pass < 8; pass++) {
         GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * SORT_BITS));
         long long *tk = ka; ka = kb; kb = tk;

@@ -32,6 +32,8 @@
 namespace gb {
 
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift);   // bh_sort.cu
+int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n);                           // bh_sort.cu
+extern const int sort_small_max_n;
 int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);                                // scan.cu
 int whfast_accel_with_list(grav_b200_ctx *c, const double *d_jx, const double *d_eta, double eps, const int *list, int nl,
                            const int *rank);                                                                              // whfast.cu
@@ -478,10 +480,15 @@ static int wh_sort(grav_b200_ctx *c, WhfastState *w)
     int *pa = w->perm[0].as<int>(), *pb = w->perm[1].as<int>();
     wh_dist_kernel<<<WH_GRID(n, 256)>>>(n, w->JX(), st, ka, pa);
     WH_LAUNCHED();
-    for (int pass = 0; pass < 8; pass++) {
-        GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * 8));
-        long long *tk = ka; ka = kb; kb = tk;
-        int *tp = pa; pa = pb; pb = tp;
+    static const bool two_launch = getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH") && atoi(getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH")) != 0;
+    if (n <= sort_small_max_n && !two_launch) {
+        GB_TRY(radix_sort_small(c, ka, pa, kb, pb, n));       // 8 passes: the result is back in ka / pa
+    } else {
+        for (int pass = 0; pass < 8; pass++) {
+            GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * 8));
+            long long *tk = ka; ka = kb; kb = tk;
+            int *tp = pa; pa = pb; pb = tp;
+        }
     }
     const int o = w->cur ^ 1;
     wh_gather_kernel<<<WH_GRID(n, 256)>>>(n, pa, w->JX(), w->JV(), w->M(), w->IDS(), w->jx[o].as<double>(), w->jv[o].as<double>(),

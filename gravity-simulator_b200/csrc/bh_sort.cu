@@ -123,7 +123,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ROUNDS = 16;                              // pairs per thread: 4096-pair tiles (large n)
 constexpr int SORT_ROUNDS_SMALL = 4;                         // 1024-pair tiles, n <= SORT_SMALL_MAX_N
-constexpr int SORT_SMALL_MAX_N = 128 * SORT_THREADS * SORT_ROUNDS_SMALL;   // <= 128 tiles: every CTA scans the histogram itself
+constexpr int SORT_SMALL_MAX_N = 128 * SORT_THREADS * SORT_ROUNDS_SMALL;   // SMALL_MAX_TILES tiles   // <= 128 tiles: every CTA scans the histogram itself
 // Small-n variant (FUSED): a 1e5-particle sort has only 25 of the big tiles -- a sixth of the SMs -- and its three scan
 // launches per pass cost more than the sort kernels.  With 1024-pair tiles the work spreads over ~100 CTAs, the histogram
 // is laid out [tile][digit] and each scatter CTA derives its own output offsets from it (<= 128 x 256 counters, read
@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_kernel(const long 
 // (the two-launch version above needs the histogram kernel to finish first); the waits are batched so the ~100 loads
 // per thread overlap.
 constexpr unsigned SMALL_VALID = 0x80000000u;
+constexpr int SMALL_MAX_TILES = 128;
 
 template <int ROUNDS>
 __global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const long long *__restrict__ keys_in,
@@ -538,15 +539,16 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const lon
             run += t;
         }
         st_status(status + (size_t)tile * SORT_RADIX + d, (unsigned)run | SMALL_VALID);
-        // every tile's count of digit d: batches of 8 independent loads, then spin only on the stragglers
+        // every tile's count of digit d ([tile][digit] layout: a warp reads 128 contiguous bytes per tile): batches of 32
+        // independent loads (one L2 round trip each batch), then spin only on the stragglers
         int tot = 0, before = 0;
-        for (int t0 = 0; t0 < num_tiles; t0 += 8) {
-            unsigned w8[8];
+        for (int t0 = 0; t0 < num_tiles; t0 += 32) {
+            unsigned w16[32];
 #pragma unroll
-            for (int j = 0; j < 8; j++) w8[j] = (t0 + j < num_tiles) ? ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d) : SMALL_VALID;
+            for (int j = 0; j < 32; j++) w16[j] = (t0 + j < num_tiles) ? ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d) : SMALL_VALID;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                unsigned sv = w8[j];
+            for (int j = 0; j < 32; j++) {
+                unsigned sv = w16[j];
                 while (!(sv & SMALL_VALID)) sv = ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d);
                 const int h = (int)(sv & ~SMALL_VALID);
                 tot += h;
@@ -593,19 +595,162 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const lon
     }
 }
 
+// The same eight passes inside ONE kernel: the wait for all tiles' counts already is a grid-wide rendezvous, a second
+// one (atomic arrival counter) after the scatter lets the next pass start without a kernel boundary.  All CTAs are
+// resident (<= 128), so the barriers cannot deadlock.  A graph node costs ~6 us on this path, a barrier ~2 us.
+template <int ROUNDS>
+__global__ void __launch_bounds__(SORT_THREADS) sort_small_all_kernel(long long *ka, int *pa, long long *kb, int *pb, int n, int num_tiles, unsigned *status_all,
+                                                                      unsigned *bar)
+{
+    constexpr int TILE = SORT_THREADS * ROUNDS;
+    constexpr int WCHUNK = 32 * ROUNDS;
+    __shared__ long long skeys[TILE];
+    __shared__ int svals[TILE];
+    __shared__ int wcnt[SORT_WARPS][SORT_RADIX];
+    __shared__ int gbase[SORT_RADIX];
+    __shared__ int wsum[SORT_WARPS], wsum2[SORT_WARPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int tile = blockIdx.x;
+    const int base = tile * TILE;
+    const int tile_n = min(TILE, n - base);
+  for (int pass = 0; pass < 8; pass++) {
+    // buffers alternate; pairs written by other CTAs during the previous pass are read past L1 (__ldcg)
+    const long long *keys_in = (pass & 1) ? kb : ka;
+    const int *vals_in = (pass & 1) ? pb : pa;
+    long long *keys_out = (pass & 1) ? ka : kb;
+    int *vals_out = (pass & 1) ? pa : pb;
+    unsigned *status = status_all + (size_t)pass * SMALL_MAX_TILES * SORT_RADIX;
+    const int shift = pass * SORT_BITS;
+    for (int d = lane; d < SORT_RADIX; d += 32) wcnt[warp][d] = 0;
+    __syncwarp();
+
+    long long k[ROUNDS];
+    int v[ROUNDS];
+    unsigned short rk[ROUNDS];
+    const int wbase = warp * WCHUNK;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        k[r] = valid ? __ldcg(keys_in + base + li) : 0;
+        v[r] = valid ? __ldcg(vals_in + base + li) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        const bool valid = li < tile_n;
+        const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
+        const unsigned same = __match_any_sync(0xffffffffu, d);
+        const int leader = 31 - __clz(same);
+        int prev = 0;
+        if (valid && lane == leader) {
+            prev = wcnt[warp][d];
+            wcnt[warp][d] = prev + __popc(same);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rk[r] = (unsigned short)(prev + __popc(same & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    {
+        const int d = tid;
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            const int t = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += t;
+        }
+        st_status(status + (size_t)tile * SORT_RADIX + d, (unsigned)run | SMALL_VALID);
+        // every tile's count of digit d ([tile][digit] layout: a warp reads 128 contiguous bytes per tile): batches of 32
+        // independent loads (one L2 round trip each batch), then spin only on the stragglers
+        int tot = 0, before = 0;
+        for (int t0 = 0; t0 < num_tiles; t0 += 32) {
+            unsigned w16[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) w16[j] = (t0 + j < num_tiles) ? ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d) : SMALL_VALID;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                unsigned sv = w16[j];
+                while (!(sv & SMALL_VALID)) sv = ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d);
+                const int h = (int)(sv & ~SMALL_VALID);
+                tot += h;
+                if (t0 + j < tile) before += h;
+            }
+        }
+        int inc = run, ginc = tot;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, s2);
+            const int g = __shfl_up_sync(0xffffffffu, ginc, s2);
+            if (lane >= s2) { inc += t; ginc += g; }
+        }
+        if (lane == 31) { wsum[warp] = inc; wsum2[warp] = ginc; }
+        __syncthreads();
+        int woff = 0, goff = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            woff += (w < warp) ? wsum[w] : 0;
+            goff += (w < warp) ? wsum2[w] : 0;
+        }
+        const int dstart = woff + inc - run;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) wcnt[w][d] += dstart;
+        gbase[d] = (goff + ginc - tot) + before - dstart;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int li = wbase + r * 32 + lane;
+        if (li < tile_n) {
+            const int slot = wcnt[warp][digit_of(k[r], shift)] + rk[r];
+            skeys[slot] = k[r];
+            svals[slot] = v[r];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < tile_n; i += SORT_THREADS) {
+        const long long kk = skeys[i];
+        const int pos = gbase[digit_of(kk, shift)] + i;
+        keys_out[pos] = kk;
+        vals_out[pos] = svals[i];
+    }
+    // grid barrier: every tile's output must be in memory before anybody reads it as the next pass's input
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(bar + pass, 1u);
+        while (ld_status(bar + pass) < (unsigned)num_tiles) { }
+    }
+    __syncthreads();
+  }
+}
+
 // All 8 passes of a small sort (n <= SORT_SMALL_MAX_N): one memset + 8 launches; ka/pa hold the result.
 int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
 {
     DevTree &t = c->tree;
     constexpr int TILE = SORT_THREADS * SORT_ROUNDS_SMALL;
     const int num_tiles = (n + TILE - 1) / TILE;
-    const size_t words = (size_t)8 * num_tiles * SORT_RADIX;
+    const size_t words = (size_t)8 * SMALL_MAX_TILES * SORT_RADIX + 8;      // 1 MiB of status words + 8 barrier counters
     GB_TRY(t.hist.reserve(sizeof(int) * words));
     unsigned *status = t.hist.as<unsigned>();
     GB_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * words, c->stream));
+    static const bool per_pass = getenv("GRAV_B200_SORT_SMALL_PER_PASS") && atoi(getenv("GRAV_B200_SORT_SMALL_PER_PASS")) != 0;
+    if (!per_pass) {
+        sort_small_all_kernel<SORT_ROUNDS_SMALL><<<num_tiles, SORT_THREADS, 0, c->stream>>>(ka, pa, kb, pb, n, num_tiles, status,
+                                                                                           status + words - 8);
+        GB_LAUNCH_CHECK();
+        count_launch();
+        return GRAV_B200_OK;        // even number of passes: the result is in ka / pa
+    }
     for (int pass = 0; pass < 8; pass++) {
         sort_small_pass_kernel<SORT_ROUNDS_SMALL><<<num_tiles, SORT_THREADS, 0, c->stream>>>(ka, pa, n, pass * SORT_BITS, num_tiles,
-                                                                                            status + (size_t)pass * num_tiles * SORT_RADIX, kb, pb);
+                                                                                            status + (size_t)pass * SMALL_MAX_TILES * SORT_RADIX, kb, pb);
         GB_LAUNCH_CHECK();
         count_launch();
         long long *tk = ka; ka = kb; kb = tk;

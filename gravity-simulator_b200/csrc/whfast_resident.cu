@@ -28,6 +28,7 @@
 // replayed up to that step, which is finished "carefully" (flags -> stable compaction -> new eta), exactly like
 // the serial reference build does (ascending index order, src/system.c:444-528).
 #include "internal.cuh"
+#include "whfast_device.cuh"
 
 namespace gb {
 
@@ -46,7 +47,7 @@ struct WhfastState {
     DevBuf jx[2], jv[2], m[2], ids[2];       // ping-pong: [cur] is live, [cur^1] is the gather target
     int cur = 0;
     DevBuf eta, etaM, keys[2], perm[2];
-    DevBuf flag, rank, list;                 // massive flags, exclusive scan (n+1), massive indices
+    DevBuf flag, rank, list, ulist;          // massive flags, exclusive scan (n+1), massive indices (sorted / as appended)
     DevBuf tab, tabinfo, cstate, texp;       // jacobi<->cartesian skeleton outputs
     DevBuf bad, status;                      // per-particle removal flags; status[0] = primary slot, [1] = first bad step,
                                              // [2] = removal count, [3] = error bits
@@ -75,7 +76,7 @@ void whfast_state_free(grav_b200_ctx *c)
     WhfastState *w = (WhfastState *)c->wh;
     if (!w) return;
     DevBuf *bufs[] = {&w->jx[0], &w->jx[1], &w->jv[0], &w->jv[1], &w->m[0], &w->m[1], &w->ids[0], &w->ids[1], &w->eta, &w->etaM,
-                      &w->keys[0], &w->keys[1], &w->perm[0], &w->perm[1], &w->flag, &w->rank, &w->list, &w->tab, &w->tabinfo,
+                      &w->keys[0], &w->keys[1], &w->perm[0], &w->perm[1], &w->flag, &w->rank, &w->list, &w->ulist, &w->tab, &w->tabinfo,
                       &w->cstate, &w->texp, &w->bad, &w->status, &w->ck_jx, &w->ck_jv, &w->ck_m, &w->ck_ids};
     for (DevBuf *b : bufs) b->release();
     if (w->h_status) cudaFreeHost(w->h_status);
@@ -102,12 +103,14 @@ __global__ void wh_primary_kernel(int n, const int *__restrict__ ids, int primar
 }
 
 // key = bit pattern of the distance (non-negative doubles order like their bit patterns); the primary gets 0 (:1277)
-__global__ void __launch_bounds__(256) wh_dist_kernel(int n, const double *__restrict__ pos, int *__restrict__ status,
-                                                      long long *__restrict__ keys, int *__restrict__ perm)
+// slot: status word holding the primary's index; reset_slot (>= 0): word to re-arm for the gather kernel of this step
+__global__ void __launch_bounds__(256) wh_dist_kernel(int n, const double *__restrict__ pos, int *__restrict__ status, int slot,
+                                                      int reset_slot, long long *__restrict__ keys, int *__restrict__ perm)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int p = status[0];
+    int p = status[slot];
+    if (i == 0 && reset_slot >= 0) status[reset_slot] = 0x7f7f7f7f;
     if (p < 0 || p >= n) {          // id not present: the host turns this into GRAV_VALUE_ERROR
         if (i == 0) atomicOr(&status[3], 1);
         p = 0;
@@ -122,11 +125,14 @@ __global__ void __launch_bounds__(256) wh_gather_kernel(int n, const int *__rest
                                                         const double *__restrict__ b_in, const double *__restrict__ m_in,
                                                         const int *__restrict__ ids_in, double *__restrict__ a_out,
                                                         double *__restrict__ b_out, double *__restrict__ m_out,
-                                                        int *__restrict__ ids_out)
+                                                        int *__restrict__ ids_out, int *__restrict__ status, int next_slot,
+                                                        int *__restrict__ ulist)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t s = (size_t)perm[i];
+    if (ids_in[s] == 0) atomicMin(&status[next_slot], i);        // where the next sort finds particle id 0 (:1234-1251)
+    if (m_in[s] != 0.0) ulist[atomicAdd(&status[6], 1)] = i;     // massive particles, order fixed by wh_skel_kernel
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         a_out[3 * (size_t)i + k] = a_in[3 * s + k];
@@ -155,6 +161,7 @@ __global__ void wh_eta_skel_kernel(int K, const int *__restrict__ list, const do
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     status[5] += 1;          // step tag for the drift kernel that follows (kernel parameters are frozen inside a graph)
+    status[6] = 0;           // massive indices appended by the gather kernel are not used on this path
     double e = 0.0;
     for (int k = 0; k < K; k++) {
         const double mk = m[list[k]];
@@ -162,6 +169,46 @@ __global__ void wh_eta_skel_kernel(int K, const int *__restrict__ list, const do
         etaM[k] = e;
     }
 }
+// Small-K path: the gather kernel appended the massive indices in arbitrary order; one CTA ranks them (K <= 1024),
+// re-arms the append counter and runs the eta recurrence.
+constexpr int WH_SKEL_MAX_K = 1024;
+__global__ void __launch_bounds__(256) wh_skel_kernel(int K, const int *__restrict__ ulist, int *__restrict__ list,
+                                                      const double *__restrict__ m, double *__restrict__ etaM, int *__restrict__ status)
+{
+    __shared__ int s_u[WH_SKEL_MAX_K];
+    const int cnt = status[6];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_u[k] = (k < cnt) ? ulist[k] : 0x7fffffff;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int mine = s_u[k];
+        int r = 0;
+        for (int j = 0; j < K; j++) r += (s_u[j] < mine);        // indices are distinct
+        list[r] = mine;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (cnt != K) atomicOr(&status[3], 2);                   // the massive count changed behind the host's back
+        status[6] = 0;
+        status[5] += 1;
+        double e = 0.0;
+        for (int k = 0; k < K; k++) {
+            const double mk = m[list[k]];
+            e = (k == 0) ? mk : add(e, mk);
+            etaM[k] = e;
+        }
+    }
+}
+// number of massive particles with index < i (list sorted ascending)
+__device__ __forceinline__ int massive_before(const int *__restrict__ list, int K, int i)
+{
+    int lo = 0, hi = K;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (list[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // eta at particle i, given cnt = number of massive particles with index <= i
 __device__ __forceinline__ double eta_at(const double *__restrict__ etaM, int cnt) { return cnt > 0 ? etaM[cnt - 1] : 0.0; }
 
@@ -205,15 +252,27 @@ __global__ void __launch_bounds__(128) wh_drift_kernel(int n, double *__restrict
                                                        const double *__restrict__ m, const int *__restrict__ rank,
                                                        const double *__restrict__ etaM, double *__restrict__ eta, double G,
                                                        double dt, int remove_invalid, char *__restrict__ bad,
-                                                       int *__restrict__ status)
+                                                       int *__restrict__ status, const int *__restrict__ list, int K,
+                                                       int *__restrict__ rank_out, int *__restrict__ flag_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double eta_i = eta_at(etaM, rank[i + 1]);
+    int r0, r1;     // massive particles with index < i, <= i
+    if (list) {     // small-K path: rank / flag arrays are produced here for the kernels that follow
+        const int f = m[i] != 0.0;
+        r0 = massive_before(list, K, i);
+        r1 = r0 + f;
+        rank_out[i] = r0;
+        flag_out[i] = f;
+        if (i == n - 1) { rank_out[n] = r1; flag_out[n] = 0; }
+    } else {
+        r0 = rank[i]; r1 = rank[i + 1];
+    }
+    const double eta_i = eta_at(etaM, r1);
     eta[i] = eta_i;
     bad[i] = 0;
     if (i == 0) return;
-    const double eta_im1 = eta_at(etaM, rank[i]);
+    const double eta_im1 = eta_at(etaM, r0);
     const double gm = dvd(mul(mul(G, m[0]), eta_i), eta_im1);                       // :459
     const double x0 = jx[3 * (size_t)i], x1 = jx[3 * (size_t)i + 1], x2 = jx[3 * (size_t)i + 2];
     const double v0 = jv[3 * (size_t)i], v1 = jv[3 * (size_t)i + 1], v2 = jv[3 * (size_t)i + 2];
@@ -368,13 +427,15 @@ __device__ __forceinline__ double wh_run(double cm, double eta, int len, int hi,
     return cm;
 }
 
-__global__ void wh_j2c_skel_kernel(int n, int K, const int *__restrict__ list, const double *__restrict__ m,
-                                   const double *__restrict__ etaM, const double *__restrict__ jx, const double *__restrict__ jv,
-                                   double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ tab,
-                                   int *__restrict__ tabinfo, double *__restrict__ texp)
+// pair_out != nullptr (massless method, K <= WH_PAIR_MAX_K): afterwards the warp also tabulates, for every gap g between
+// massive particles, the sum over massive pairs straddling the gap that every massless target of that gap subtracts
+// (src/integrator_whfast.c:1225-1252: same loops, same order, evaluated once instead of once per target).
+constexpr int WH_PAIR_MAX_K = 64;
+__device__ __forceinline__ void wh_j2c_skel_lane(int c, int n, int K, const int *__restrict__ list, const double *__restrict__ m,
+                                                 const double *__restrict__ etaM, const double *__restrict__ jx,
+                                                 const double *__restrict__ jv, double4 *posm, double *__restrict__ vel,
+                                                 double *__restrict__ tab, int *__restrict__ tabinfo, double *__restrict__ texp)
 {
-    const int c = threadIdx.x;
-    if (blockIdx.x != 0 || c >= 6) return;
     double cm = mul(eta_at(etaM, K), ld_jac(jx, jv, 0, c));                 // :742-748
     int hi = n - 1;
     bool reached_zero = false;
@@ -384,6 +445,7 @@ __global__ void wh_j2c_skel_kernel(int n, int K, const int *__restrict__ list, c
         cm = wh_run(cm, e_k, hi - mi, hi, k + 1, c, tab, tabinfo, texp);
         if (mi == 0) { reached_zero = true; break; }
         const double j = ld_jac(jx, jv, mi, c);
+        if (c == 0) reinterpret_cast<double *>(posm)[4 * (size_t)mi + 3] = m[mi];
         const double t = dvd(sub(cm, mul(m[mi], j)), e_k);                  // :754
         st_cart(posm, vel, mi, c, add(j, t));                               // :757
         cm = mul(eta_at(etaM, k), t);                                       // :760
@@ -391,20 +453,51 @@ __global__ void wh_j2c_skel_kernel(int n, int K, const int *__restrict__ list, c
     }
     if (!reached_zero) cm = wh_run(cm, 0.0, hi, hi, 0, c, tab, tabinfo, texp);   // particle 0 itself is massless
     else if (c == 0) { for (int q = 0; q < 12; q++) tabinfo[q] = 0; }
+    if (c == 0) reinterpret_cast<double *>(posm)[4 * 0 + 3] = m[0];
     st_cart(posm, vel, 0, c, dvd(cm, m[0]));                                // :765-771
 }
 
-__global__ void __launch_bounds__(256) wh_j2c_fill_kernel(int n, int K, const int *__restrict__ flag, const int *__restrict__ rank,
-                                                          const int *__restrict__ list, const double *__restrict__ m,
-                                                          const double *__restrict__ jx, const double *__restrict__ jv,
-                                                          const double *__restrict__ tab, const int *__restrict__ tabinfo,
-                                                          const double *__restrict__ texp, double4 *__restrict__ posm,
-                                                          double *__restrict__ vel)
+__global__ void __launch_bounds__(256) wh_j2c_skel_kernel(int n, int K, const int *__restrict__ list, const double *__restrict__ m,
+                                                          const double *__restrict__ etaM, const double *__restrict__ jx, double *jv,
+                                                          double4 *posm, double *__restrict__ vel, double *__restrict__ tab,
+                                                          int *__restrict__ tabinfo, double *__restrict__ texp, double G, double eps3,
+                                                          const double *__restrict__ eta, double *acc, double h,
+                                                          double *__restrict__ pair_out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    reinterpret_cast<double *>(posm)[4 * (size_t)i + 3] = m[i];
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (threadIdx.x < 6) wh_j2c_skel_lane(threadIdx.x, n, K, list, m, etaM, jx, jv, posm, vel, tab, tabinfo, texp);
+    if (!pair_out) return;
+    // massless method, few massive bodies: the rest of the step for the MASSIVE particles happens here too, one warp per
+    // item -- K accelerations + kicks (:1006-1128, :409-422) and the K + 1 gap sums the massless targets will subtract
+    __threadfence_block();
+    __syncthreads();
+    for (int it = warp; it < 2 * K + 1; it += nwarps) {
+        if (it < K) {
+            whfast_accel_massive_warp(it, posm, G, jx, eta, eps3, list, K, acc);
+            __syncwarp();
+            if (lane < 3) {
+                const size_t e = 3 * (size_t)list[it] + lane;
+                jv[e] = add(jv[e], mul(acc[e], h));
+            }
+        } else {
+            const int g = it - K;
+            const V3 s = whfast_gap_pair_sum_warp(g, posm, G, eps3, list, K);
+            if (lane == 0) { pair_out[3 * g + 0] = s.x; pair_out[3 * g + 1] = s.y; pair_out[3 * g + 2] = s.z; }
+        }
+    }
+}
+
+// Cartesian state of massless particle i from the skeleton's tables (massive particles and particle 0 are written by
+// the skeleton itself, masses included)
+__device__ __forceinline__ void wh_j2c_fill_one(int i, int n, int K, const int *__restrict__ flag, const int *__restrict__ rank,
+                                                const int *__restrict__ list, const double *__restrict__ m,
+                                                const double *__restrict__ jx, const double *jv,
+                                                const double *__restrict__ tab, const int *__restrict__ tabinfo,
+                                                const double *__restrict__ texp, double4 *posm, double *__restrict__ vel)
+{
     if (i == 0 || flag[i]) return;
+    reinterpret_cast<double *>(posm)[4 * (size_t)i + 3] = m[i];
     const int r = rank[i];
     const int hi = (r < K) ? list[r] - 1 : n - 1;
     const int j = hi - i;
@@ -416,6 +509,40 @@ __global__ void __launch_bounds__(256) wh_j2c_fill_kernel(int n, int K, const in
         else if (j < WH_KMAX) t = tab[((size_t)r * (WH_KMAX + 1) + j) * 6 + c];
         else t = texp[6 * (size_t)i + c];
         st_cart(posm, vel, i, c, add(ld_jac(jx, jv, i, c), t));
+    }
+}
+
+__global__ void __launch_bounds__(256) wh_j2c_fill_kernel(int n, int K, const int *__restrict__ flag, const int *__restrict__ rank,
+                                                          const int *__restrict__ list, const double *__restrict__ m,
+                                                          const double *__restrict__ jx, const double *__restrict__ jv,
+                                                          const double *__restrict__ tab, const int *__restrict__ tabinfo,
+                                                          const double *__restrict__ texp, double4 *__restrict__ posm,
+                                                          double *__restrict__ vel)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) wh_j2c_fill_one(i, n, K, flag, rank, list, m, jx, jv, tab, tabinfo, texp, posm, vel);
+}
+
+// Massless method only: the rest of the step for particle i in one kernel -- its Cartesian state, its interaction
+// acceleration (which reads the particle's own record and the massive particles', all final after the skeleton kernel)
+// and its kick.  With the pairwise method a target reads every other particle's record, so the three stay separate.
+__global__ void __launch_bounds__(128) wh_tail_kernel(int n, int K, const int *__restrict__ flag, const int *__restrict__ rank,
+                                                      const int *__restrict__ list, const double *__restrict__ m,
+                                                      const double *__restrict__ jx, double *jv,
+                                                      const double *__restrict__ tab, const int *__restrict__ tabinfo,
+                                                      const double *__restrict__ texp, double4 *posm,
+                                                      double *__restrict__ vel, double G, const double *__restrict__ eta, double eps3,
+                                                      double *acc, double h, const double *__restrict__ pair_sum)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (pair_sum && flag[i]) return;     // massive particles were finished by the skeleton kernel
+    wh_j2c_fill_one(i, n, K, flag, rank, list, m, jx, jv, tab, tabinfo, texp, posm, vel);
+    whfast_accel_one(i, n, posm, G, jx, eta, eps3, list, K, rank, acc, pair_sum);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const size_t e = 3 * (size_t)i + k;
+        jv[e] = add(jv[e], mul(acc[e], h));
     }
 }
 
@@ -460,25 +587,35 @@ static int wh_reserve(grav_b200_ctx *c, WhfastState *w, int n)
     GB_TRY(w->etaM.reserve(b1));
     GB_TRY(w->texp.reserve(2 * b3));
     GB_TRY(w->bad.reserve((size_t)n + 16));
-    GB_TRY(w->status.reserve(sizeof(int) * 8));
+    GB_TRY(w->status.reserve(sizeof(int) * 16));
+    GB_TRY(w->ulist.reserve(sizeof(int) * (size_t)n));
     GB_TRY(w->ck_jx.reserve(b3)); GB_TRY(w->ck_jv.reserve(b3)); GB_TRY(w->ck_m.reserve(b1));
     GB_TRY(w->ck_ids.reserve(sizeof(int) * (size_t)n));
     if (!w->h_status) GB_CUDA(cudaMallocHost(&w->h_status, sizeof(int) * 16));
     return GRAV_B200_OK;
 }
 
-// Stable sort of the live arrays by distance of `A` from the particle with id 0; A/B are the live position/velocity
-// arrays (Cartesian at start-up, Jacobi inside the loop).
+// Index of the particle with id 0 in the live arrays -> status[8 + cur] (start-up, after a removal, after a restore;
+// inside the loop the gather kernel of the previous step provides it).
+static int wh_find_primary(grav_b200_ctx *c, WhfastState *w)
+{
+    int *slot = w->status.as<int>() + 8 + w->cur;
+    GB_CUDA(cudaMemsetAsync(slot, 0x7f, sizeof(int), c->stream));
+    wh_primary_kernel<<<WH_GRID(c->n, 256)>>>(c->n, w->IDS(), 0, slot);
+    WH_LAUNCHED();
+    return GRAV_B200_OK;
+}
+
+// Stable sort of the live arrays by distance of the live position array from the particle with id 0 (Cartesian
+// positions at start-up, Jacobi positions inside the loop).  The gather also records where id 0 went and appends the
+// massive particles for the skeleton kernel.
 static int wh_sort(grav_b200_ctx *c, WhfastState *w)
 {
-    const int n = c->n;
+    const int n = c->n, par = w->cur;
     int *st = w->status.as<int>();
-    GB_CUDA(cudaMemsetAsync(st, 0x7f, sizeof(int), c->stream));
-    wh_primary_kernel<<<WH_GRID(n, 256)>>>(n, w->IDS(), 0, st);
-    WH_LAUNCHED();
     long long *ka = w->keys[0].as<long long>(), *kb = w->keys[1].as<long long>();
     int *pa = w->perm[0].as<int>(), *pb = w->perm[1].as<int>();
-    wh_dist_kernel<<<WH_GRID(n, 256)>>>(n, w->JX(), st, ka, pa);
+    wh_dist_kernel<<<WH_GRID(n, 256)>>>(n, w->JX(), st, 8 + par, 8 + (par ^ 1), ka, pa);
     WH_LAUNCHED();
     static const bool two_launch = getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH") && atoi(getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH")) != 0;
     if (n <= sort_small_max_n && !two_launch) {
@@ -490,9 +627,9 @@ static int wh_sort(grav_b200_ctx *c, WhfastState *w)
             int *tp = pa; pa = pb; pb = tp;
         }
     }
-    const int o = w->cur ^ 1;
+    const int o = par ^ 1;
     wh_gather_kernel<<<WH_GRID(n, 256)>>>(n, pa, w->JX(), w->JV(), w->M(), w->IDS(), w->jx[o].as<double>(), w->jv[o].as<double>(),
-                                          w->m[o].as<double>(), w->ids[o].as<int>());
+                                          w->m[o].as<double>(), w->ids[o].as<int>(), st, 8 + o, w->ulist.as<int>());
     WH_LAUNCHED();
     w->cur = o;
     return GRAV_B200_OK;
@@ -524,9 +661,10 @@ static int wh_massive(grav_b200_ctx *c, WhfastState *w, bool count_massive)
 static int wh_j2c(grav_b200_ctx *c, WhfastState *w, const double *d_jv)
 {
     const int n = c->n;
-    wh_j2c_skel_kernel<<<1, 32, 0, c->stream>>>(n, w->K, w->list.as<int>(), w->M(), w->etaM.as<double>(), w->JX(), d_jv,
-                                                c->posm.as<double4>(), c->vel.as<double>(), w->tab.as<double>(),
-                                                w->tabinfo.as<int>(), w->texp.as<double>());
+    wh_j2c_skel_kernel<<<1, 32, 0, c->stream>>>(n, w->K, w->list.as<int>(), w->M(), w->etaM.as<double>(), w->JX(),
+                                                const_cast<double *>(d_jv), c->posm.as<double4>(), c->vel.as<double>(),
+                                                w->tab.as<double>(), w->tabinfo.as<int>(), w->texp.as<double>(), c->G, 0.0,
+                                                nullptr, nullptr, 0.0, nullptr);
     WH_LAUNCHED();
     wh_j2c_fill_kernel<<<WH_GRID(n, 256)>>>(n, w->K, w->flag.as<int>(), w->rank.as<int>(), w->list.as<int>(), w->M(), w->JX(), d_jv,
                                             w->tab.as<double>(), w->tabinfo.as<int>(), w->texp.as<double>(),
@@ -549,6 +687,7 @@ static int wh_accel_kick(grav_b200_ctx *c, WhfastState *w, double h)
 static int wh_check_status(grav_b200_ctx *c, WhfastState *w)
 {
     if (w->h_status[3] & 1) { set_error("Primary particle ID not found in system"); return GRAV_B200_EINVAL; }
+    if (w->h_status[3] & 2) { set_error("whfast: the number of massive particles changed inside a batch"); return GRAV_B200_ECUDA; }
     (void)c;
     return GRAV_B200_OK;
 }
@@ -557,18 +696,41 @@ static int wh_check_status(grav_b200_ctx *c, WhfastState *w)
 static int wh_step_front(grav_b200_ctx *c, WhfastState *w, double dt)
 {
     GB_TRY(wh_sort(c, w));
-    GB_TRY(wh_massive(c, w, false));
+    const bool small_k = w->K <= WH_SKEL_MAX_K;
+    if (small_k) {
+        wh_skel_kernel<<<1, 256, 0, c->stream>>>(w->K, w->ulist.as<int>(), w->list.as<int>(), w->M(), w->etaM.as<double>(),
+                                                 w->status.as<int>());
+        WH_LAUNCHED();
+    } else {
+        GB_TRY(wh_massive(c, w, false));
+    }
     wh_drift_kernel<<<WH_GRID(c->n, 128)>>>(c->n, w->JX(), w->JV(), w->M(), w->rank.as<int>(), w->etaM.as<double>(),
                                             w->eta.as<double>(), c->G, dt, w->remove_invalid ? 1 : 0, w->bad.as<char>(),
-                                            w->status.as<int>());
+                                            w->status.as<int>(), small_k ? w->list.as<int>() : nullptr, w->K, w->rank.as<int>(),
+                                            w->flag.as<int>());
     WH_LAUNCHED();
     return GRAV_B200_OK;
 }
 // back half: Jacobi -> Cartesian, acceleration, kick (:329-340)
 static int wh_step_back(grav_b200_ctx *c, WhfastState *w, double dt)
 {
-    GB_TRY(wh_j2c(c, w, w->JV()));
-    GB_TRY(wh_accel_kick(c, w, dt));
+    if (w->method == GRAV_B200_METHOD_MASSLESS) {
+        const int n = c->n;
+        const double eps3 = w->eps * w->eps * w->eps;
+        double *pairs = w->K <= WH_PAIR_MAX_K ? w->cstate.as<double>() : nullptr;     // cstate (6 (K+1) doubles) is free after begin()
+        wh_j2c_skel_kernel<<<1, pairs ? 256 : 32, 0, c->stream>>>(n, w->K, w->list.as<int>(), w->M(), w->etaM.as<double>(), w->JX(),
+                                                                  w->JV(), c->posm.as<double4>(), c->vel.as<double>(),
+                                                                  w->tab.as<double>(), w->tabinfo.as<int>(), w->texp.as<double>(),
+                                                                  c->G, eps3, w->eta.as<double>(), c->acc.as<double>(), dt, pairs);
+        WH_LAUNCHED();
+        wh_tail_kernel<<<WH_GRID(n, 128)>>>(n, w->K, w->flag.as<int>(), w->rank.as<int>(), w->list.as<int>(), w->M(), w->JX(), w->JV(),
+                                            w->tab.as<double>(), w->tabinfo.as<int>(), w->texp.as<double>(), c->posm.as<double4>(),
+                                            c->vel.as<double>(), c->G, w->eta.as<double>(), eps3, c->acc.as<double>(), dt, pairs);
+        WH_LAUNCHED();
+    } else {
+        GB_TRY(wh_j2c(c, w, w->JV()));
+        GB_TRY(wh_accel_kick(c, w, dt));
+    }
     w->last_dt = dt;
     return GRAV_B200_OK;
 }
@@ -642,6 +804,7 @@ static int wh_remove_flagged(grav_b200_ctx *c, WhfastState *w, int n_removed)
     GB_TRY(wh_massive(c, w, true));
     wh_eta_fill_kernel<<<WH_GRID(n_new, 256)>>>(n_new, w->rank.as<int>(), w->etaM.as<double>(), w->eta.as<double>());
     WH_LAUNCHED();
+    GB_TRY(wh_find_primary(c, w));      // the compaction moved the particles and flipped the live buffers
     return GRAV_B200_OK;
 }
 
@@ -700,6 +863,8 @@ int grav_b200_ctx_whfast_begin(grav_b200_ctx *c, const int *particle_ids, int me
         GB_CUDA(e);
     }
     GB_TRY(wh_reset_batch_status(c, w));
+    GB_CUDA(cudaMemsetAsync(w->status.as<int>() + 6, 0, sizeof(int), c->stream));
+    GB_TRY(wh_find_primary(c, w));
     GB_TRY(wh_sort(c, w));                                   // :242, on the Cartesian positions
     GB_TRY(wh_read_status(c, w));
     // sorted Cartesian state back into posm / vel
@@ -753,6 +918,7 @@ int grav_b200_ctx_whfast_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
         GB_CUDA(cudaMemcpyAsync(w->M(), w->ck_m.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         GB_CUDA(cudaMemcpyAsync(w->IDS(), w->ck_ids.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         GB_TRY(wh_reset_batch_status(c, w));
+        GB_TRY(wh_find_primary(c, w));
         GB_TRY(wh_steps_plain_or_graph(c, w, dt, first_bad, use_graph));
         GB_TRY(wh_reset_batch_status(c, w));
         GB_TRY(wh_step_front(c, w, dt));

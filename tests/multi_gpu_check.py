@@ -1,5 +1,5 @@
 """Multi-GPU parity check, one process per GPU:  torchrun --nproc-per-node N tests/multi_gpu_check.py
-Sharded direct sum / Barnes-Hut / leapfrog against the single-GPU result computed on every rank."""
+Sharded direct sum / Barnes-Hut / leapfrog / Euler-Cromer / RK4 against the single-GPU result computed on every rank."""
 import os
 import sys
 from pathlib import Path
@@ -57,6 +57,16 @@ def main():
         rel = lambda p, q: float(np.max(np.linalg.norm(p - q, axis=1) / np.linalg.norm(p, axis=1)))
         ex, ev = rel(single.positions(), multi.positions()), rel(single.velocities(), multi.velocities())
         check(f"n={n} leapfrog 5 steps: sharded vs single max rel x {ex:.1e} v {ev:.1e} <= 1e-12", ex <= 1e-12 and ev <= 1e-12)
+        for c in (single, multi):
+            c.leapfrog_end()
+        # Euler-Cromer and RK4 on the sharded state with Barnes-Hut forces: bit-identical to the single-GPU run
+        for integ in ("euler_cromer", "rk4"):
+            for c in (single, multi):
+                c.set_system(x, m, G, v)
+                c.fixed_begin(integ, "barnes_hut", 0.01, 0.5, 1)
+                c.fixed_steps(dt, 3)
+            check(f"n={n} {integ} + barnes_hut 3 steps: sharded == single (bit-exact)",
+                  np.array_equal(single.positions(), multi.positions()) and np.array_equal(single.velocities(), multi.velocities()))
         e1, eN = single.energy(), multi.energy()
         check(f"n={n} energy: sharded vs single rel diff {abs(e1 - eN) / abs(e1):.1e}", abs(e1 - eN) <= 1e-13 * abs(e1))
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")

@@ -58,6 +58,7 @@ struct DSArgs {
     double *acc;              // AoS [3n], indexed by particle id
     double *partials;         // [grid][2][3][IB]
     int NB, NT;               // target blocks, source tiles
+    int skip_special;         // fast kernel: leave the diagonal / padded tiles to direct_sum_special_kernel
 };
 
 template <int TI>
@@ -169,7 +170,7 @@ direct_sum_kernel(const DSArgs p)
 
         // stream the source tiles through shared memory (the second CTA of the SM computes meanwhile)
         for (int jt = jt0; jt < jt1; jt++) {
-            if (!CHECK && tile_is_special(jt, p.n_src, blk_lo, blk_hi)) continue;   // block-uniform
+            if (!CHECK && p.skip_special && tile_is_special(jt, p.n_src, blk_lo, blk_hi)) continue;   // block-uniform
             __syncthreads();
             tile[tid] = p.src[(size_t)jt * DS_TJ + tid];
             if (MASSLESS) {
@@ -315,7 +316,13 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
     // Small source counts (and the massless method) run everything through the checked loop in one kernel;
     // otherwise fast kernel + special-tile kernel.
     static const int checked_max_tiles = getenv("GRAV_B200_DS_CHECKED_TILES") ? atoi(getenv("GRAV_B200_DS_CHECKED_TILES")) : 64;
-    const bool all_checked = MASSLESS || a.NT <= checked_max_tiles;
+    // With a softening length the self term needs no check at all: dx = dy = dz = 0 gives r2 = eps^2 > 0, a finite
+    // s = m / eps^3 and the contribution fma(s, 0, a) = a exactly; padding sources (m = 0 at the origin) contribute
+    // fma(0, dx, a) = a.  The fast loop then runs over every tile, at every N (eps >= 1e-30 keeps m / eps^3 far from
+    // overflow).  Only eps = 0 needs the checked loop / the special-tile kernel.
+    const bool softened = !MASSLESS && a.eps2 >= 1e-60;
+    const bool all_checked = !softened && (MASSLESS || a.NT <= checked_max_tiles);
+    a.skip_special = softened ? 0 : 1;
     const long long U = (long long)a.NB * a.NT;
     long long grid = (long long)c->sm_count * 2;
     if (grid > DS_FIXUP_MAX_CONTRIB) grid = DS_FIXUP_MAX_CONTRIB;   // the fix-up kernel's per-block contributor table
@@ -334,7 +341,7 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
         GB_LAUNCH_CHECK();
         count_launch();
     }
-    if (!all_checked) {
+    if (!all_checked && !softened) {
         // one target per thread here: 4x the CTAs of the main decomposition, one or two tiles each
         direct_sum_special_kernel<IB><<<(n_tgt + DS_BLOCK - 1) / DS_BLOCK, DS_BLOCK, 0, c->stream>>>(a);
         GB_LAUNCH_CHECK();

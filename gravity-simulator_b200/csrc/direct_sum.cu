@@ -94,8 +94,10 @@ __device__ __forceinline__ void tile_interactions(const double4 *__restrict__ ti
                                                   const double (&zi)[TI], const int (&ii)[TI],
                                                   const bool (&alt)[TI], double eps2, Acc<TI> &a)
 {
+    // checked loops stop at the last real source (the massless method has a handful of sources in a 256-wide tile)
+    const int jcount = CHECK ? min(DS_TJ, n_src - j_base) : DS_TJ;
 #pragma unroll 2
-    for (int j = 0; j < DS_TJ; j++) {
+    for (int j = 0; j < jcount; j++) {
         const double4 pj = tile[j];
         int jid = j_base + j;
         double altm = 0.0;
@@ -300,10 +302,9 @@ __global__ void __launch_bounds__(DS_BLOCK) direct_sum_fixup_kernel(const DSArgs
 
 constexpr int DS_TI = 4;
 
-template <bool MASSLESS>
-static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
+template <bool MASSLESS, int TI>
+static int launch_direct_sum_t(grav_b200_ctx *c, DSArgs &a)
 {
-    constexpr int TI = DS_TI;
     constexpr int IB = DS_BLOCK * TI;
     const int n_tgt = a.i_hi - a.i_lo;
     if (n_tgt <= 0) return GRAV_B200_OK;
@@ -348,6 +349,18 @@ static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
         count_launch();
     }
     return GRAV_B200_OK;
+}
+
+// Few targets: with 1024-target blocks a small system has fewer work units than the GPU has CTA slots (N = 4096: 64 units
+// of 33 us each on 296 slots).  One target per thread gives four times as many, shorter units.
+template <bool MASSLESS>
+static int launch_direct_sum(grav_b200_ctx *c, DSArgs &a)
+{
+    const long long nb4 = (a.i_hi - a.i_lo + DS_BLOCK * DS_TI - 1) / (DS_BLOCK * DS_TI);
+    const long long nt = (a.n_src + DS_TJ - 1) / DS_TJ;
+    static const int ti1_units = getenv("GRAV_B200_DS_TI1_UNITS") ? atoi(getenv("GRAV_B200_DS_TI1_UNITS")) : 0;
+    if (nb4 * nt < (ti1_units > 0 ? ti1_units : c->sm_count)) return launch_direct_sum_t<MASSLESS, 1>(c, a);
+    return launch_direct_sum_t<MASSLESS, DS_TI>(c, a);
 }
 
 int direct_sum_pairwise(grav_b200_ctx *c, double eps)

@@ -266,7 +266,7 @@ def run_b200_arm(args):
         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and n == (1 << 20)) else None,
         "traffic_note": "dram__bytes_read+write of one launch at N=2^20, ncu --set full (profiles/r1_direct_sum_n1m.txt); "
                         "algorithmic bytes = 32 B x N sources + 24 B x N results = 58.7 MB",
-        "kernel": "direct_sum_kernel<4,false,false> (+ fix-up and special-tile kernels, <0.5% of the stage)", "kernel_ms": k_ms,
+        "kernel": "direct_sum_kernel<4,false,false> (+ the fix-up kernel of split target blocks, <0.1% of the stage)", "kernel_ms": k_ms,
         "convention": f"{FLOP_PER_INTERACTION} flop per ordered interaction; peak = {peak_src} "
                       f"(= {peak_mhz:.0f} MHz x 148 SM x 64 DFMA lanes x 2)",
         "fp64_pipe_util": FP64_OPS_PER_INTERACTION * k_inter / (k_ms * 1e-3) / (peak_tf * 1e12 / 2.0),

@@ -54,6 +54,7 @@ struct WhfastState {
     DevBuf ck_jx, ck_jv, ck_m, ck_ids;       // checkpoint of the Jacobi state at the start of a batch
     int *h_status = nullptr;                 // pinned
     int K = 0;                               // massive particles
+    int skel_max_k = 1024, pair_max_k = 64;  // path thresholds (WH_SKEL_MAX_K / WH_PAIR_MAX_K; lowered by tests through the environment)
     // two consecutive steps captured as one CUDA graph (the ping-pong buffers are back in place after two), per
     // starting parity; valid for one (n, K, dt)
     cudaGraphExec_t pair_exec[2] = {nullptr, nullptr};
@@ -696,7 +697,7 @@ static int wh_check_status(grav_b200_ctx *c, WhfastState *w)
 static int wh_step_front(grav_b200_ctx *c, WhfastState *w, double dt)
 {
     GB_TRY(wh_sort(c, w));
-    const bool small_k = w->K <= WH_SKEL_MAX_K;
+    const bool small_k = w->K <= w->skel_max_k;
     if (small_k) {
         wh_skel_kernel<<<1, 256, 0, c->stream>>>(w->K, w->ulist.as<int>(), w->list.as<int>(), w->M(), w->etaM.as<double>(),
                                                  w->status.as<int>());
@@ -717,7 +718,7 @@ static int wh_step_back(grav_b200_ctx *c, WhfastState *w, double dt)
     if (w->method == GRAV_B200_METHOD_MASSLESS) {
         const int n = c->n;
         const double eps3 = w->eps * w->eps * w->eps;
-        double *pairs = w->K <= WH_PAIR_MAX_K ? w->cstate.as<double>() : nullptr;     // cstate (6 (K+1) doubles) is free after begin()
+        double *pairs = w->K <= w->pair_max_k ? w->cstate.as<double>() : nullptr;     // cstate (6 (K+1) doubles) is free after begin()
         wh_j2c_skel_kernel<<<1, pairs ? 256 : 32, 0, c->stream>>>(n, w->K, w->list.as<int>(), w->M(), w->etaM.as<double>(), w->JX(),
                                                                   w->JV(), c->posm.as<double4>(), c->vel.as<double>(),
                                                                   w->tab.as<double>(), w->tabinfo.as<int>(), w->texp.as<double>(),
@@ -844,6 +845,11 @@ int grav_b200_ctx_whfast_begin(grav_b200_ctx *c, const int *particle_ids, int me
     const int n = c->n;
     GB_TRY(wh_reserve(c, w, n));
     w->method = method; w->eps = eps; w->remove_invalid = remove_invalid_particles != 0; w->ready = false; w->cur = 0;
+    {   // test hooks: force the large-K code paths with a handful of massive bodies
+        const char *e1 = getenv("GRAV_B200_WHFAST_SKEL_MAX_K"), *e2 = getenv("GRAV_B200_WHFAST_PAIR_MAX_K");
+        w->skel_max_k = e1 ? (atoi(e1) < WH_SKEL_MAX_K ? atoi(e1) : WH_SKEL_MAX_K) : WH_SKEL_MAX_K;
+        w->pair_max_k = e2 ? (atoi(e2) < WH_PAIR_MAX_K ? atoi(e2) : WH_PAIR_MAX_K) : WH_PAIR_MAX_K;
+    }
     c->lf_ready = false;
     // live arrays <- Cartesian state (x unpacked from posm, v, m) + ids
     wh_unpack_kernel<<<WH_GRID(n, 256)>>>(n, c->posm.as<double4>(), w->JX());

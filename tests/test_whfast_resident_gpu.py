@@ -108,3 +108,24 @@ def test_resident_whfast_ids_and_errors(gb, oracle, ics):
             c.whfast_begin(1.0, "massless", ids=np.arange(1, n + 1, dtype=np.int32))
         with pytest.raises(gb.GravB200Error, match="whfast_begin"):
             c.whfast_steps(1.0, 1)
+
+
+@pytest.mark.parametrize("skel_max_k,pair_max_k", [(4, 64), (1024, 4), (0, 0)])
+def test_resident_whfast_large_k_paths(gb, oracle, ics, monkeypatch, skel_max_k, pair_max_k):
+    """The paths for many massive bodies (massive list by flag/scan instead of the one-CTA ranking; massive targets and
+    straddling-pair sums per thread instead of per warp / per gap), forced with the nine bodies of the solar system."""
+    monkeypatch.setenv("GRAV_B200_WHFAST_SKEL_MAX_K", str(skel_max_k))
+    monkeypatch.setenv("GRAV_B200_WHFAST_PAIR_MAX_K", str(pair_max_k))
+    x, v, m, G = ics.asteroid_belt(700, 17, grazers=6)
+    ref = oracle.whfast_integrate(x, v, m, G, 180.0, 180.0 * 9, "massless", 0.0, True)
+    assert ref["m"].shape[0] < m.shape[0]
+    _same(_run_gpu(gb, x, v, m, G, 180.0, 9, "massless", 0.0, True), ref)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_resident_whfast_tiny_systems(gb, oracle, ics, n):
+    xs, vs, ms, G = ics.solar_system()
+    x, v, m = xs[:n].copy(), vs[:n].copy(), ms[:n].copy()
+    for method in ("pairwise", "massless"):
+        ref = oracle.whfast_integrate(x, v, m, G, 2.0, 2.0 * 5, method, 0.0, True)
+        _same(_run_gpu(gb, x, v, m, G, 2.0, 5, method, 0.0, True), ref)

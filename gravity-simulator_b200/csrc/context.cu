@@ -266,6 +266,7 @@ int grav_b200_ctx_set_system(grav_b200_ctx *c, int n, const double *x, const dou
     c->hi = (int)(((long long)(c->rank + 1) * n) / c->world);
     c->lf_ready = false;
     c->fixed_integrator = 0;
+    c->mlist_valid = false;
     const size_t b3 = sizeof(double) * 3 * (size_t)n;
     GB_TRY(c->posm.reserve(sizeof(double4) * (size_t)c->n_pad));
     GB_TRY(c->acc.reserve(b3));

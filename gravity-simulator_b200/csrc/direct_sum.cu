@@ -454,27 +454,35 @@ int massive_list(grav_b200_ctx *c, int *n_massive_out)
     int *flag = c->mflag.as<int>();
     int *rank = c->mrank.as<int>();
     const int nb = (n + 255) / 256;
-    GB_CUDA(cudaMemsetAsync(flag + n, 0, sizeof(int), c->stream));
-    massless_flags_kernel<<<nb, 256, 0, c->stream>>>(c->posm.as<double4>(), n, flag);
-    GB_LAUNCH_CHECK();
-    count_launch();
-    GB_TRY(exclusive_scan_int(c, flag, rank, n + 1, c->misc));
-    int n_massive = 0;
-    GB_CUDA(cudaMemcpyAsync(&n_massive, rank + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    GB_CUDA(cudaStreamSynchronize(c->stream));
+    int n_massive = c->mlist_count;
+    if (!c->mlist_valid) {
+        // which particles are massive only changes with the masses (set_system): inside a resident integration the flags,
+        // ranks and the count are reused and every later call just refreshes the packed source records
+        GB_CUDA(cudaMemsetAsync(flag + n, 0, sizeof(int), c->stream));
+        massless_flags_kernel<<<nb, 256, 0, c->stream>>>(c->posm.as<double4>(), n, flag);
+        GB_LAUNCH_CHECK();
+        count_launch();
+        GB_TRY(exclusive_scan_int(c, flag, rank, n + 1, c->misc));
+        GB_CUDA(cudaMemcpyAsync(&n_massive, rank + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        c->mlist_count = n_massive;
+    }
     const int pad = ((n_massive + SRC_PAD - 1) / SRC_PAD) * SRC_PAD;
     GB_TRY(c->msrc.reserve(sizeof(double4) * (size_t)(pad ? pad : SRC_PAD)));
     GB_TRY(c->msrc_id.reserve(sizeof(int) * (size_t)(pad ? pad : SRC_PAD)));
     GB_TRY(c->msrc_altm.reserve(sizeof(double) * (size_t)(pad ? pad : SRC_PAD)));
     if (pad) {
-        GB_CUDA(cudaMemsetAsync(c->msrc.p, 0, sizeof(double4) * (size_t)pad, c->stream));
-        GB_CUDA(cudaMemsetAsync(c->msrc_id.p, 0xff, sizeof(int) * (size_t)pad, c->stream));
-        GB_CUDA(cudaMemsetAsync(c->msrc_altm.p, 0, sizeof(double) * (size_t)pad, c->stream));
+        if (!c->mlist_valid) {      // padding entries; the real ones are rewritten by every compaction
+            GB_CUDA(cudaMemsetAsync(c->msrc.p, 0, sizeof(double4) * (size_t)pad, c->stream));
+            GB_CUDA(cudaMemsetAsync(c->msrc_id.p, 0xff, sizeof(int) * (size_t)pad, c->stream));
+            GB_CUDA(cudaMemsetAsync(c->msrc_altm.p, 0, sizeof(double) * (size_t)pad, c->stream));
+        }
         massless_compact_kernel<<<nb, 256, 0, c->stream>>>(c->posm.as<double4>(), n, flag, rank, c->msrc.as<double4>(),
                                                          c->msrc_id.as<int>(), c->msrc_altm.as<double>());
         GB_LAUNCH_CHECK();
         count_launch();
     }
+    c->mlist_valid = true;
     *n_massive_out = n_massive;
     return GRAV_B200_OK;
 }

@@ -115,6 +115,8 @@ struct grav_b200_ctx {
     gb::DevBuf misc;      // small scratch (reductions)
     // massless method scratch
     gb::DevBuf msrc, msrc_id, msrc_altm, mflag, mrank;
+    bool mlist_valid = false;     // mflag / mrank / the massive count describe the resident masses (reset by set_system)
+    int mlist_count = 0;
     gb::DevTree tree;
 
     // leapfrog bookkeeping

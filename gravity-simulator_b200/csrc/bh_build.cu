@@ -16,7 +16,7 @@
 //               exclusive prefix sum over sorted positions of "children created by expanded nodes starting
 //               here" and same_start(u) counts the children of u's expanded ancestors that start at s_u.
 //               id(child k of u) = first_child(u) + k.
-//   moments     levels deepest-first, one thread per expanded node, children in id order; a leaf child adds
+//   moments     levels deepest-first, eight lanes per expanded node, children in id order; a leaf child adds
 //               its particles one at a time in sorted order, an expanded child adds its finished sums;
 //               separate multiply and add (no FMA) and IEEE division, as the reference's x86-64 build
 //               does.  Leaves keep mass = com = 0 (src/linear_octree.c:567-570).
@@ -118,73 +118,102 @@ __global__ void __launch_bounds__(128) emit_kernel(ExpRec *__restrict__ rec, int
     }
 }
 
-__global__ void __launch_bounds__(256) first_child_kernel(ExpRec *__restrict__ rec, int ne, const int *__restrict__ P)
-{
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < ne) rec[u].first_child = 1 + P[rec[u].b[0]] + rec[u].same_start;
-}
-
-__global__ void __launch_bounds__(256) fill_children_kernel(const ExpRec *__restrict__ rec, int ne, int *__restrict__ np,
-                                                           int *__restrict__ nchild, int *__restrict__ first,
-                                                           int *__restrict__ fc)
+// Numbering and node arrays in one pass over the expanded records.  first_child(u) = 1 + P[s_u] + same_start(u); the id of
+// u itself is first_child(parent) + rank (the parent's first_child is recomputed from the parent's record, so no kernel
+// boundary is needed).  A parent writes count / first position of all its children and the leaf defaults of the children
+// that stay leaves; an expanded child writes its own child count and first-child id (same rule as emit_kernel decides
+// who is expanded), so no entry has two writers.
+__global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *__restrict__ rec, int ne, int n, int max_leaf,
+                                                        const int *__restrict__ P, int *__restrict__ np,
+                                                        int *__restrict__ nchild, int *__restrict__ first, int *__restrict__ fc)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= ne) return;
     const ExpRec r = rec[u];
+    const int fcu = 1 + P[r.b[0]] + r.same_start;
+    int id = 0;
+    if (r.parent >= 0) {
+        const int ps = rec[r.parent].b[0], pss = rec[r.parent].same_start;
+        id = 1 + P[ps] + pss + r.rank;
+    } else {
+        np[0] = n; first[0] = 0;
+    }
+    rec[u].first_child = fcu;
+    rec[u].id = id;
+    nchild[id] = r.nch;
+    fc[id] = fcu;
+    const int l = r.level + 1;
     for (int k = 0; k < r.nch; k++) {
-        const int id = r.first_child + k;
-        np[id] = r.b[k + 1] - r.b[k];
-        first[id] = r.b[k];
-        nchild[id] = 0;    // leaf unless fill_own_kernel says otherwise
-        fc[id] = -1;       // the reference leaves this uninitialised for leaves
+        const int cid = fcu + k, cnt = r.b[k + 1] - r.b[k];
+        np[cid] = cnt;
+        first[cid] = r.b[k];
+        if (!(cnt > max_leaf && l < MAX_LEVEL)) {
+            nchild[cid] = 0;
+            fc[cid] = -1;       // the reference leaves this uninitialised for leaves
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) fill_own_kernel(ExpRec *__restrict__ rec, int ne, int n, int *__restrict__ np,
-                                                      int *__restrict__ nchild, int *__restrict__ first,
-                                                      int *__restrict__ fc)
-{
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= ne) return;
-    ExpRec r = rec[u];
-    const int id = (r.parent < 0) ? 0 : rec[r.parent].first_child + r.rank;
-    rec[u].id = id;
-    nchild[id] = r.nch;
-    fc[id] = r.first_child;
-    if (r.parent < 0) { np[0] = n; first[0] = 0; }
-}
-
+// Eight lanes per expanded node, one per child: the loads of the children's contributions (a leaf's particle through
+// perm -> posm, an expanded child's finished sums) go out together; then every lane of the octet adds the items up in
+// the reference's order (children in id order, the particles of a leaf one at a time), so the sums are bit-identical to
+// the serial loop.  Leaves with several particles (max_leaf > 1, or duplicates at level 21) are read in the ordered
+// phase by all eight lanes (same address: one transaction).
 __global__ void __launch_bounds__(128) moments_kernel(const ExpRec *__restrict__ rec, int begin, int count,
                                                      const int *__restrict__ perm, const double4 *__restrict__ posm,
                                                      const int *__restrict__ nchild, double *__restrict__ mass,
                                                      double *__restrict__ mtd, double *__restrict__ cx,
                                                      double *__restrict__ cy, double *__restrict__ cz)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const ExpRec r = rec[begin + t];
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = gt >> 3, o = gt & 7;
+    if (t >= count) return;                      // whole octets leave together
+    const ExpRec *r = rec + begin + t;
+    const int nch = r->nch, fcid = r->first_child;
+    const int g0 = (threadIdx.x & 31) & ~7;
+    const unsigned gmask = 0xffu << g0;
+    double im = 0.0, ix = 0.0, iy = 0.0, iz = 0.0;
+    int start = 0, cnt = 0, multi = 0;
+    if (o < nch) {
+        const int cid = fcid + o;
+        start = r->b[o];
+        cnt = r->b[o + 1] - start;
+        if (nchild[cid] != 0) {
+            im = mass[cid];
+            ix = mtd[3 * (size_t)cid + 0]; iy = mtd[3 * (size_t)cid + 1]; iz = mtd[3 * (size_t)cid + 2];
+        } else if (cnt == 1) {
+            const double4 q = posm[perm[start]];
+            im = q.w;
+            ix = __dmul_rn(q.w, q.x); iy = __dmul_rn(q.w, q.y); iz = __dmul_rn(q.w, q.z);
+        } else {
+            multi = 1;
+        }
+    }
     double tot = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int k = 0; k < r.nch; k++) {
-        const int cid = r.first_child + k;
-        if (nchild[cid] == 0) {
-            for (int p = r.b[k]; p < r.b[k + 1]; p++) {
+    for (int k = 0; k < nch; k++) {
+        const int mk = __shfl_sync(gmask, multi, k, 8);
+        if (!mk) {
+            tot = __dadd_rn(tot, __shfl_sync(gmask, im, k, 8));
+            sx = __dadd_rn(sx, __shfl_sync(gmask, ix, k, 8));
+            sy = __dadd_rn(sy, __shfl_sync(gmask, iy, k, 8));
+            sz = __dadd_rn(sz, __shfl_sync(gmask, iz, k, 8));
+        } else {
+            const int ps = __shfl_sync(gmask, start, k, 8), pc = __shfl_sync(gmask, cnt, k, 8);
+            for (int p = ps; p < ps + pc; p++) {
                 const double4 q = posm[perm[p]];
                 tot = __dadd_rn(tot, q.w);
                 sx = __dadd_rn(sx, __dmul_rn(q.w, q.x));
                 sy = __dadd_rn(sy, __dmul_rn(q.w, q.y));
                 sz = __dadd_rn(sz, __dmul_rn(q.w, q.z));
             }
-        } else {
-            tot = __dadd_rn(tot, mass[cid]);
-            sx = __dadd_rn(sx, mtd[3 * (size_t)cid + 0]);
-            sy = __dadd_rn(sy, mtd[3 * (size_t)cid + 1]);
-            sz = __dadd_rn(sz, mtd[3 * (size_t)cid + 2]);
         }
     }
-    const int id = r.id;
-    mass[id] = tot;
-    mtd[3 * (size_t)id + 0] = sx; mtd[3 * (size_t)id + 1] = sy; mtd[3 * (size_t)id + 2] = sz;
-    cx[id] = __ddiv_rn(sx, tot); cy[id] = __ddiv_rn(sy, tot); cz[id] = __ddiv_rn(sz, tot);
+    if (o == 0) {
+        const int id = r->id;
+        mass[id] = tot;
+        mtd[3 * (size_t)id + 0] = sx; mtd[3 * (size_t)id + 1] = sy; mtd[3 * (size_t)id + 2] = sz;
+        cx[id] = __ddiv_rn(sx, tot); cy[id] = __ddiv_rn(sy, tot); cz[id] = __ddiv_rn(sz, tot);
+    }
 }
 
 // Packed per-node record for the walk.  Reference mode reproduces the walk's key fetch
@@ -343,21 +372,16 @@ int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double bo
     GB_CUDA(cudaMemsetAsync(t.node_cz.p, 0, md, c->stream));
     ExpRec *rec = t.exp_rec.as<ExpRec>();
     const int eb = (ne + 255) / 256;
-    first_child_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, t.wscan.as<int>());
+    fill_nodes_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, n, max_leaf, t.wscan.as<int>(), t.node_np.as<int>(), t.node_nch.as<int>(),
+                                                t.node_first.as<int>(), t.node_fc.as<int>());
     GB_LAUNCH_CHECK();
-    fill_children_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
-                                                   t.node_fc.as<int>());
-    GB_LAUNCH_CHECK();
-    fill_own_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, n, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
-                                              t.node_fc.as<int>());
-    GB_LAUNCH_CHECK();
-    count_launch(3);
+    count_launch();
 
     // moments, deepest level first
     for (int l = levels - 1; l >= 0; l--) {
         const int begin = level_off[l], count = level_off[l + 1] - begin;
         if (count <= 0) continue;
-        moments_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(rec, begin, count, t.perm.as<int>(), c->posm.as<double4>(),
+        moments_kernel<<<(8 * count + 127) / 128, 128, 0, c->stream>>>(rec, begin, count, t.perm.as<int>(), c->posm.as<double4>(),
                                                                   t.node_nch.as<int>(), t.node_mass.as<double>(),
                                                                   t.node_mtd.as<double>(), t.node_cx.as<double>(),
                                                                   t.node_cy.as<double>(), t.node_cz.as<double>());

@@ -26,9 +26,12 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return GRAV_B200_ECUDA;
 }
 
+uint64_t g_alloc_generation = 0;   // bumped whenever a device buffer moves: captured CUDA graphs hold raw pointers
+
 int DevBuf::reserve(size_t bytes)
 {
     if (bytes <= cap && p) return GRAV_B200_OK;
+    __atomic_fetch_add(&g_alloc_generation, (uint64_t)1, __ATOMIC_RELAXED);
     if (bytes == 0) bytes = 256;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
     // grow geometrically so per-call scratch settles quickly
@@ -46,6 +49,7 @@ int DevBuf::reserve(size_t bytes)
 
 void DevBuf::release()
 {
+    if (p) __atomic_fetch_add(&g_alloc_generation, (uint64_t)1, __ATOMIC_RELAXED);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;

@@ -28,6 +28,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 #define GB_LAUNCH_CHECK() GB_CUDA(cudaGetLastError())
 
 extern int64_t g_launch_count;   // kernels launched by this library
+extern uint64_t g_alloc_generation;   // device-buffer (re)allocations so far (graph caches compare it)
 inline void count_launch(int k = 1) { __atomic_fetch_add(&g_launch_count, (int64_t)k, __ATOMIC_RELAXED); }
 
 // ---- geometry of the direct-sum kernel ----------------------------------------------

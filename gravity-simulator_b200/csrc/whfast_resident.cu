@@ -59,6 +59,7 @@ struct WhfastState {
     // starting parity; valid for one (n, K, dt)
     cudaGraphExec_t pair_exec[2] = {nullptr, nullptr};
     int pair_n[2] = {0, 0}, pair_K[2] = {0, 0}, pair_launches[2] = {0, 0};
+    uint64_t pair_gen[2] = {0, 0};           // g_alloc_generation at capture: a buffer that moved since invalidates the graph
     double pair_dt[2] = {0.0, 0.0};
     int method = 0;
     double eps = 0.0;
@@ -741,7 +742,8 @@ static int wh_step_back(grav_b200_ctx *c, WhfastState *w, double dt)
 static int wh_step_pair(grav_b200_ctx *c, WhfastState *w, double dt)
 {
     const int par = w->cur;
-    if (!w->pair_exec[par] || w->pair_n[par] != c->n || w->pair_K[par] != w->K || w->pair_dt[par] != dt) {
+    if (!w->pair_exec[par] || w->pair_n[par] != c->n || w->pair_K[par] != w->K || w->pair_dt[par] != dt ||
+        w->pair_gen[par] != g_alloc_generation) {
         if (w->pair_exec[par]) { cudaGraphExecDestroy(w->pair_exec[par]); w->pair_exec[par] = nullptr; }
         const int64_t l0 = g_launch_count;
         GB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -759,6 +761,7 @@ static int wh_step_pair(grav_b200_ctx *c, WhfastState *w, double dt)
         cudaGraphDestroy(graph);
         GB_CUDA(ei);
         w->pair_n[par] = c->n; w->pair_K[par] = w->K; w->pair_dt[par] = dt; w->pair_launches[par] = captured;
+        w->pair_gen[par] = g_alloc_generation;
     }
     GB_CUDA(cudaGraphLaunch(w->pair_exec[par], c->stream));
     count_launch(w->pair_launches[par]);
@@ -845,6 +848,8 @@ int grav_b200_ctx_whfast_begin(grav_b200_ctx *c, const int *particle_ids, int me
     const int n = c->n;
     GB_TRY(wh_reserve(c, w, n));
     w->method = method; w->eps = eps; w->remove_invalid = remove_invalid_particles != 0; w->ready = false; w->cur = 0;
+    for (int k = 0; k < 2; k++)      // method, eps and the flags are baked into captured steps
+        if (w->pair_exec[k]) { cudaGraphExecDestroy(w->pair_exec[k]); w->pair_exec[k] = nullptr; }
     {   // test hooks: force the large-K code paths with a handful of massive bodies
         const char *e1 = getenv("GRAV_B200_WHFAST_SKEL_MAX_K"), *e2 = getenv("GRAV_B200_WHFAST_PAIR_MAX_K");
         w->skel_max_k = e1 ? (atoi(e1) < WH_SKEL_MAX_K ? atoi(e1) : WH_SKEL_MAX_K) : WH_SKEL_MAX_K;

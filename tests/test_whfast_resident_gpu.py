@@ -129,3 +129,22 @@ def test_resident_whfast_tiny_systems(gb, oracle, ics, n):
     for method in ("pairwise", "massless"):
         ref = oracle.whfast_integrate(x, v, m, G, 2.0, 2.0 * 5, method, 0.0, True)
         _same(_run_gpu(gb, x, v, m, G, 2.0, 5, method, 0.0, True), ref)
+
+
+def test_resident_whfast_context_reuse(gb, oracle, ics):
+    """One context, several integrations back to back (different method, size and step): cached step graphs and the
+    massive-list cache must not leak from one run into the next."""
+    runs = [(ics.asteroid_belt(40, 31), "massless", 0.0, 20.0, 9), (ics.asteroid_belt(40, 31), "pairwise", 0.01, 20.0, 9),
+            (ics.asteroid_belt(900, 32), "massless", 0.0, 180.0, 7), (ics.asteroid_belt(40, 33), "massless", 0.0, 20.0, 9)]
+    with gb.Context() as c:
+        for (x, v, m, G), method, eps, dt, steps in runs:
+            c.set_system(x, m, G, v)
+            c.whfast_begin(dt, method, eps, True)
+            c.whfast_steps(dt, steps)
+            got = c.whfast_state()
+            _same(got, oracle.whfast_integrate(x, v, m, G, dt, dt * steps, method, eps, True))
+            # a massless direct-sum call on the same context afterwards uses a fresh massive list
+            c.set_system(got["x"], got["m"], G, got["v"])
+            c.acceleration("massless", 0.0)
+            a = c.accelerations()
+            assert np.array_equal(a, gb.acceleration(got["x"], got["m"], G, "massless", 0.0))

@@ -38,7 +38,7 @@ UNIT = "G interactions/s"
 FLOP_PER_INTERACTION = 20      # GPU-Gems-3 convention: 18 + rsqrt counted as 2
 FP64_OPS_PER_INTERACTION = 16  # FP64-pipe instructions our kernel actually issues per interaction
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12   # 37.2, used only if the live measurement fails
-NCU_DRAM_BYTES_PER_LAUNCH = 34179840 + 5368576   # dram read + write, profiles/r1_direct_sum_n1m.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 52571392 + 51328512   # dram read + write, profiles/r1_direct_sum_n1m_final.txt
 
 
 def parse_args():
@@ -264,7 +264,7 @@ def run_b200_arm(args):
     roofline = {
         "bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and n == (1 << 20)) else None,
-        "traffic_note": "dram__bytes_read+write of one launch at N=2^20, ncu --set full (profiles/r1_direct_sum_n1m.txt); "
+        "traffic_note": "dram__bytes_read+write of one launch at N=2^20, ncu --set full (profiles/r1_direct_sum_n1m_final.txt; includes the 28 MB of partial sums of split target blocks); "
                         "algorithmic bytes = 32 B x N sources + 24 B x N results = 58.7 MB",
         "kernel": "direct_sum_kernel<4,false,false> (+ the fix-up kernel of split target blocks, <0.1% of the stage)", "kernel_ms": k_ms,
         "convention": f"{FLOP_PER_INTERACTION} flop per ordered interaction; peak = {peak_src} "

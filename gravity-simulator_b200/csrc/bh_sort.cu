@@ -759,7 +759,6 @@ int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, in
     return GRAV_B200_OK;
 }
 
-extern const int sort_small_max_n = SORT_SMALL_MAX_N;
 
 // One stable pass on an 8-bit digit of arbitrary (key, value) arrays; scratch: t.hist / t.scan_tmp.
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift)
@@ -836,6 +835,13 @@ static int onesweep_sort(grav_b200_ctx *c, long long *ka, int *pa, long long *kb
 {
     // 4096-pair tiles: 2048- and 3072-pair tiles measured 24 % and 11 % slower at N = 2^24
     return onesweep_sort_t<SORT_ROUNDS>(c, ka, pa, kb, pb, n);
+}
+
+// Stable sort of n (key, value) pairs held in ka / pa with kb / pb as scratch; the result ends in ka / pa.
+int radix_sort_buffers(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
+{
+    if (n <= SORT_SMALL_MAX_N) return radix_sort_small(c, ka, pa, kb, pb, n);
+    return onesweep_sort(c, ka, pa, kb, pb, n);
 }
 
 // keys/perm sorted in place (8 passes ping-pong through keys_tmp/perm_tmp)

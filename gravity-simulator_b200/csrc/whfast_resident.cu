@@ -33,8 +33,7 @@
 namespace gb {
 
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift);   // bh_sort.cu
-int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n);                           // bh_sort.cu
-extern const int sort_small_max_n;
+int radix_sort_buffers(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n);                         // bh_sort.cu
 int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, DevBuf &tmp);                                // scan.cu
 int whfast_accel_with_list(grav_b200_ctx *c, const double *d_jx, const double *d_eta, double eps, const int *list, int nl,
                            const int *rank);                                                                              // whfast.cu
@@ -620,8 +619,8 @@ static int wh_sort(grav_b200_ctx *c, WhfastState *w)
     wh_dist_kernel<<<WH_GRID(n, 256)>>>(n, w->JX(), st, 8 + par, 8 + (par ^ 1), ka, pa);
     WH_LAUNCHED();
     static const bool two_launch = getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH") && atoi(getenv("GRAV_B200_SORT_SMALL_TWO_LAUNCH")) != 0;
-    if (n <= sort_small_max_n && !two_launch) {
-        GB_TRY(radix_sort_small(c, ka, pa, kb, pb, n));       // 8 passes: the result is back in ka / pa
+    if (!two_launch) {
+        GB_TRY(radix_sort_buffers(c, ka, pa, kb, pb, n));     // 8 passes: the result is back in ka / pa
     } else {
         for (int pass = 0; pass < 8; pass++) {
             GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * 8));

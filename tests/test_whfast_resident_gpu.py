@@ -43,6 +43,13 @@ def test_resident_whfast_matches_oracle(gb, oracle, ics, k, seed, steps, method,
     _same(got, ref)
 
 
+def test_resident_whfast_above_the_small_sort_limit(gb, oracle, ics):
+    """More than 131072 particles: the distance sort takes the large-n (one kernel per pass) path."""
+    x, v, m, G = ics.asteroid_belt(150000, 8)
+    ref = oracle.whfast_integrate(x, v, m, G, 180.0, 180.0 * 3, "massless", 0.0, True)
+    _same(_run_gpu(gb, x, v, m, G, 180.0, 3, "massless", 0.0, True), ref)
+
+
 def test_resident_whfast_config3_size(gb, oracle, ics):
     """Config 3 at its full size: Sun + 8 planets + 1e5 massless asteroids, dt = 180 d."""
     x, v, m, G = ics.asteroid_belt(100000, 7)

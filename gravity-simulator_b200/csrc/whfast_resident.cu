@@ -27,6 +27,13 @@
 // state; the drift kernel records the first step of the batch that flagged a particle, and only then the batch is
 // replayed up to that step, which is finished "carefully" (flags -> stable compaction -> new eta), exactly like
 // the serial reference build does (ascending index order, src/system.c:444-528).
+//
+// A step of the common case (massless method, <= 64 massive bodies, <= 131072 particles) is seven kernels, two steps
+// per CUDA graph launch:
+//   wh_dist_kernel -> sort_small_all_kernel (bh_sort.cu) -> wh_gather_kernel -> wh_skel_kernel -> wh_drift_kernel ->
+//   wh_j2c_skel_kernel (recurrence, then massive targets and gap pair sums, one warp per item) -> wh_tail_kernel
+// Larger systems, more massive bodies and the pairwise method fall back to separate flag/scan/list, fill,
+// acceleration and kick kernels (tests force those paths through GRAV_B200_WHFAST_SKEL_MAX_K / _PAIR_MAX_K).
 #include "internal.cuh"
 #include "whfast_device.cuh"
 

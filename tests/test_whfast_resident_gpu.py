@@ -155,3 +155,34 @@ def test_resident_whfast_context_reuse(gb, oracle, ics):
             c.acceleration("massless", 0.0)
             a = c.accelerations()
             assert np.array_equal(a, gb.acceleration(got["x"], got["m"], G, "massless", 0.0))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_resident_whfast_fuzz(gb, oracle, seed):
+    """Random small systems: 1-12 massive bodies of very different masses around a dominant primary, 0-400 massless
+    ones, bound and unbound orbits, close approaches, exact duplicates of positions (distance ties), random dt and
+    method.  State, order and survivors must match the oracle bit for bit.  (Runs whose oracle state contains NaN are
+    skipped: the reference's qsort comparator is not an ordering for NaN distances.)"""
+    rng = np.random.default_rng(1000 + seed)
+    nm = int(rng.integers(1, 13)); nl = int(rng.integers(0, 401))
+    method = "massless" if nl and rng.random() < 0.75 else ("pairwise" if nm + nl <= 60 else "massless")
+    G = 0.00029591220828411951
+    m = np.concatenate([[1.0], 10.0 ** rng.uniform(-9, -3, nm - 1), np.zeros(nl)])
+    n = m.shape[0]
+    a = np.concatenate([[0.0], 10.0 ** rng.uniform(-0.7, 1.5, n - 1)])
+    ph = rng.uniform(0, 2 * np.pi, n); inc = rng.normal(0, 0.2, n)
+    x = np.stack([a * np.cos(ph), a * np.sin(ph), a * np.sin(inc)], axis=1)
+    vc = np.sqrt(G / np.maximum(a, 1e-3)) * rng.uniform(0.3, 1.6, n)      # 1.41 = escape: some are unbound
+    v = np.stack([-vc * np.sin(ph), vc * np.cos(ph), vc * rng.normal(0, 0.1, n)], axis=1)
+    v[0] = 0.0
+    if n > 6:                                   # exact duplicates of a position: equal distances
+        x[n - 1] = x[n - 2]; x[n - 3] = x[n - 2]
+    order = rng.permutation(n - 1) + 1          # the primary stays first, everything else shuffled
+    x[1:], v[1:], m[1:] = x[order], v[order], m[order]
+    dt = float(10.0 ** rng.uniform(-1, 2.3)); steps = int(rng.integers(2, 8)); eps = float(rng.choice([0.0, 1e-3]))
+    # max_steps: ceil((dt * steps) / dt) can round up to steps + 1 for a random dt (the reference then takes one more,
+    # overshoot-shortened step); the comparison is about `steps` full steps
+    ref = oracle.whfast_integrate(x, v, m, G, dt, dt * steps, method, eps, True, max_steps=steps)
+    if not (np.isfinite(ref["x"]).all() and np.isfinite(ref["v"]).all()):
+        pytest.skip("oracle state is not finite for this seed")
+    _same(_run_gpu(gb, x, v, m, G, dt, steps, method, eps, True), ref)

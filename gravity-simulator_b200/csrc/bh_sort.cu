@@ -730,12 +730,32 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_small_all_kernel(long long 
   }
 }
 
+int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift);
+
 // All 8 passes of a small sort (n <= SORT_SMALL_MAX_N): one memset + 8 launches; ka/pa hold the result.
 int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, int *pb, int n)
 {
     DevTree &t = c->tree;
     constexpr int TILE = SORT_THREADS * SORT_ROUNDS_SMALL;
     const int num_tiles = (n + TILE - 1) / TILE;
+    // Both kernels below wait for every tile of the grid, so the whole grid has to be resident at once.  True for
+    // <= 128 CTAs on a full B200 (148 SMs x >= 2 CTAs); on anything smaller (a MIG slice) fall back to the
+    // histogram + scatter pair of launches per pass, which has no inter-CTA waits.
+    static int resident_ctas = -1;
+    if (resident_ctas < 0) {
+        int per_sm_all = 0, per_sm_pass = 0;
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_all, sort_small_all_kernel<SORT_ROUNDS_SMALL>, SORT_THREADS, 0));
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pass, sort_small_pass_kernel<SORT_ROUNDS_SMALL>, SORT_THREADS, 0));
+        resident_ctas = c->sm_count * (per_sm_all < per_sm_pass ? per_sm_all : per_sm_pass);
+    }
+    if (num_tiles > resident_ctas) {
+        for (int pass = 0; pass < 8; pass++) {
+            GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * SORT_BITS));
+            long long *tk = ka; ka = kb; kb = tk;
+            int *tp = pa; pa = pb; pb = tp;
+        }
+        return GRAV_B200_OK;
+    }
     const size_t words = (size_t)8 * SMALL_MAX_TILES * SORT_RADIX + 8;      // 1 MiB of status words + 8 barrier counters
     GB_TRY(t.hist.reserve(sizeof(int) * words));
     unsigned *status = t.hist.as<unsigned>();

@@ -96,6 +96,7 @@ ABI_SYMBOLS = [
     "grav_b200_acceleration_massless", "grav_b200_acceleration_barnes_hut",
     "grav_b200_whfast_acceleration_pairwise", "grav_b200_whfast_acceleration_massless",
     "grav_b200_construct_octree", "grav_b200_morton_keys", "grav_b200_set_bh_mode", "grav_b200_get_bh_mode",
+    "grav_b200_set_bh_exact", "grav_b200_get_bh_exact",
     "grav_b200_ctx_create", "grav_b200_ctx_destroy", "grav_b200_nccl_unique_id", "grav_b200_ctx_set_system",
     "grav_b200_ctx_set_positions", "grav_b200_ctx_num_particles", "grav_b200_ctx_owned_range",
     "grav_b200_ctx_acceleration", "grav_b200_ctx_get_positions", "grav_b200_ctx_get_velocities",

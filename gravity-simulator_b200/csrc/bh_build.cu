@@ -9,22 +9,33 @@
 //   discovery   breadth-first.  The root is always expanded.  The children of an expanded node of level
 //               l-1 are the maximal runs of equal (key >> 3(21-l)) in its sorted range; a child is
 //               expanded iff it holds more than max_leaf particles and l < 21.  Eight lanes per expanded
-//               node find the octant boundaries by binary search; the next level's records are
-//               placed with a prefix sum, so record order is deterministic (by start position).
+//               node find the octant boundaries by binary search and write the records of the children that
+//               are expanded in turn; a CTA takes the slots for its 32 nodes' children with one atomic.
 //   numbering   the reference serves expanded nodes in (start position, level) order and gives each all of
 //               its children at once, so   first_child(u) = 1 + P[s_u] + same_start(u)   where P is the
 //               exclusive prefix sum over sorted positions of "children created by expanded nodes starting
 //               here" and same_start(u) counts the children of u's expanded ancestors that start at s_u.
-//               id(child k of u) = first_child(u) + k.
+//               id(child k of u) = first_child(u) + k.  Ids depend on positions only, never on the order of
+//               the records inside a level, so the atomic slot allocation above does not show in the result.
 //   moments     levels deepest-first, eight lanes per expanded node, children in id order; a leaf child adds
 //               its particles one at a time in sorted order, an expanded child adds its finished sums;
 //               separate multiply and add (no FMA) and IEEE division, as the reference's x86-64 build
 //               does.  Leaves keep mass = com = 0 (src/linear_octree.c:567-570).
+//
+// Round 2: NO host synchronisation anywhere in the build.  Level populations, the record and node totals, the box
+// width and the per-level cell sizes stay on the device (TreeMeta); every kernel is launched with a grid derived from
+// an upper bound and loops over the device-side count.  Buffers are sized from n (records: 2n, nodes: 3n, times
+// `slack`); a tree that does not fit -- only pathologically deep chains do that -- raises a flag in TreeMeta that the
+// next synchronising call reports (GRAV_B200_ETREE), and the host-pointer entries retry with twice the room.
+// The node arrays of LinearOctree (src/linear_octree.h:20-57) are no longer produced on the hot path: the walk records
+// (two 32-byte planes) are written directly, and construct_octree() derives the arrays from them on demand.
 #include "internal.cuh"
 
 namespace gb {
 
 constexpr int MAX_LEVEL = 21;
+constexpr int EXPAND_THREADS = 256;                  // 32 nodes (octets) per CTA round
+constexpr int COUNT_MASK = (1 << WALK_COUNT_BITS) - 1;
 
 struct ExpRec {       // one expanded (= has children) node, 64 bytes
     int b[9];         // child k covers sorted positions [b[k], b[k+1]); before expansion b[0] = s, b[1] = e
@@ -42,203 +53,262 @@ int exclusive_scan_int(grav_b200_ctx *c, const int *d_in, int *d_out, int n, Dev
 int bh_keys(grav_b200_ctx *c, const double *box_center, double box_width, bool want_unsorted);
 int radix_sort_pairs(grav_b200_ctx *c);
 
-__global__ void root_init_kernel(ExpRec *rec, int n)
+__global__ void tree_init_kernel(ExpRec *rec, TreeMeta *meta, int n)
 {
-    ExpRec r;
-    for (int k = 0; k < 9; k++) r.b[k] = 0;
-    r.b[0] = 0; r.b[1] = n;
-    r.level = 0; r.parent = -1; r.rank = 0; r.same_start = 0; r.nch = 0; r.first_child = 1; r.id = 0;
-    rec[0] = r;
+    if (threadIdx.x < 24) {
+        meta->lvl_cnt[threadIdx.x] = threadIdx.x == 0 ? 1 : 0;
+        meta->lvl_off[threadIdx.x] = 0;
+    }
+    if (threadIdx.x == 0) {
+        meta->num_expanded = 0; meta->num_nodes = 0; meta->levels = 0; meta->overflow = 0;
+        ExpRec r;
+        for (int k = 0; k < 9; k++) r.b[k] = 0;
+        r.b[0] = 0; r.b[1] = n;
+        r.level = 0; r.parent = -1; r.rank = 0; r.same_start = 0; r.nch = 0; r.first_child = 1; r.id = 0;
+        rec[0] = r;
+    }
 }
 
-// Eight lanes per expanded node, one per octant: lane o finds the first position of the node's range whose level-l
-// digit is >= o (all keys of the range share the higher bits), so the eight binary searches -- chains of dependent L2
-// loads -- run side by side instead of one after the other (16 x 25 us -> 16 x 6 us of build time at N = 60000).  The
-// non-empty octants, in order, are the children.
-__global__ void __launch_bounds__(128) expand_kernel(ExpRec *__restrict__ rec, int begin, int count,
-                                                    const long long *__restrict__ K, int max_leaf,
-                                                    int *__restrict__ W, int *__restrict__ nexp)
+// One level of the discovery.  Eight lanes per expanded node, one per octant: lane o finds the first position of the
+// node's range whose level-l digit is >= o (all keys of the range share the higher bits), so the eight binary searches --
+// chains of dependent L2 loads -- run side by side.  The non-empty octants, in order, are the children; those that hold
+// more than max_leaf particles get a record in the next level.  Record slots: the CTA adds up what its 32 nodes need and
+// takes them with ONE atomicAdd on the next level's counter (an atomic per node would serialise ~10^6 operations on one
+// address at N = 2^24).
+__global__ void __launch_bounds__(EXPAND_THREADS) expand_kernel(ExpRec *__restrict__ rec, TreeMeta *__restrict__ meta, int l,
+                                                               const long long *__restrict__ K, int max_leaf,
+                                                               int *__restrict__ W, int ne_cap)
 {
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = gt >> 3, o = gt & 7;
-    if (t >= count) {
-        if (t == count && o == 0) nexp[t] = 0;   // sentinel so the scan also yields the total
-        return;                                   // count * 8 is a multiple of 8: whole octets leave together
-    }
-    ExpRec *r = rec + begin + t;
-    const int s = r->b[0], e = r->b[1];
-    const int l = r->level + 1, shift = 3 * (MAX_LEVEL - l);
-    // lower bound of digit o in [s, e)
-    int lo = s, hi = e;
-    if (o > 0) {
-        while (lo < hi) {
-            const int mid = lo + ((hi - lo) >> 1);
-            if ((int)((K[mid] >> shift) & 7) < o) lo = mid + 1; else hi = mid;
-        }
-    }
-    const int lane = threadIdx.x & 31, g0 = lane & ~7;
+    __shared__ int s_warp_tot[EXPAND_THREADS / 32];
+    __shared__ int s_base;
+    const int begin = meta->lvl_off[l];
+    int count = meta->lvl_cnt[l];
+    if (begin + count > ne_cap) count = max(0, ne_cap - begin);   // overflow (flagged below): those records were never written
+    const int next_begin = begin + count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta->lvl_off[l + 1] = next_begin;
+    const int o = threadIdx.x & 7, oct = threadIdx.x >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g0 = lane & ~7;
     const unsigned gmask = 0xffu << g0;
-    const int up = __shfl_down_sync(gmask, lo, 1, 8);
-    const int end = (o == 7) ? e : up;
-    const bool nonempty = end > lo;
-    const bool grows = nonempty && (end - lo > max_leaf) && l < MAX_LEVEL;
-    const unsigned ne_mask = (__ballot_sync(gmask, nonempty) >> g0) & 0xffu;
-    const unsigned gr_mask = (__ballot_sync(gmask, grows) >> g0) & 0xffu;
-    const int nch = __popc(ne_mask);
-    if (nonempty) r->b[__popc(ne_mask & ((1u << o) - 1u))] = lo;
-    // slots nch .. 8 hold the end of the range (lane o takes slot nch + o; nch >= 1, so 8 lanes cover them)
-    if (nch + o <= 8) r->b[nch + o] = e;
-    if (o == 0) {
-        r->nch = nch;
-        nexp[t] = __popc(gr_mask);
-        atomicAdd(&W[s], nch);
+    const int cl = l + 1, shift = 3 * (MAX_LEVEL - cl);            // level of the children
+    for (int t0 = blockIdx.x * (EXPAND_THREADS / 8); t0 < count; t0 += gridDim.x * (EXPAND_THREADS / 8)) {   // CTA-uniform
+        const int t = t0 + oct;
+        const bool valid = t < count;
+        ExpRec *r = rec + begin + (valid ? t : 0);
+        int s = 0, e = 0, lo = 0, end = 0, nch = 0, my_rank = 0, same_start = 0;
+        unsigned gr_mask = 0;
+        bool grows = false;
+        if (valid) {                                               // whole octets take this branch together
+            s = r->b[0]; e = r->b[1];
+            same_start = r->same_start;
+            lo = s;
+            int hi = e;
+            if (o > 0) {
+                while (lo < hi) {
+                    const int mid = lo + ((hi - lo) >> 1);
+                    if ((int)((K[mid] >> shift) & 7) < o) lo = mid + 1; else hi = mid;
+                }
+            }
+            const int up = __shfl_down_sync(gmask, lo, 1, 8);
+            end = (o == 7) ? e : up;
+            const bool nonempty = end > lo;
+            grows = nonempty && (end - lo > max_leaf) && cl < MAX_LEVEL;
+            const unsigned ne_mask = (__ballot_sync(gmask, nonempty) >> g0) & 0xffu;
+            gr_mask = (__ballot_sync(gmask, grows) >> g0) & 0xffu;
+            nch = __popc(ne_mask);
+            my_rank = __popc(ne_mask & ((1u << o) - 1u));
+            if (nonempty) r->b[my_rank] = lo;
+            // slots nch .. 8 hold the end of the range (lane o takes slot nch + o; nch >= 1, so 8 lanes cover them)
+            if (nch + o <= 8) r->b[nch + o] = e;
+            if (o == 0) {
+                r->nch = nch;
+                atomicAdd(&W[s], nch);
+            }
+        }
+        // record slots of the expanded children: prefix over the CTA's 32 octets
+        const int g = __popc(gr_mask);                             // same on the 8 lanes of an octet, 0 for idle octets
+        const int q0 = __shfl_sync(0xffffffffu, g, 0), q1 = __shfl_sync(0xffffffffu, g, 8),
+                  q2 = __shfl_sync(0xffffffffu, g, 16), q3 = __shfl_sync(0xffffffffu, g, 24);
+        const int in_warp = (g0 >= 8 ? q0 : 0) + (g0 >= 16 ? q1 : 0) + (g0 >= 24 ? q2 : 0);
+        if (lane == 0) s_warp_tot[warp] = q0 + q1 + q2 + q3;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < EXPAND_THREADS / 32; w++) tot += s_warp_tot[w];
+            s_base = tot > 0 ? atomicAdd(&meta->lvl_cnt[cl], tot) : 0;
+        }
+        __syncthreads();
+        if (grows) {
+            int slot = next_begin + s_base + in_warp + __popc(gr_mask & ((1u << o) - 1u));
+            for (int w = 0; w < warp; w++) slot += s_warp_tot[w];
+            if (slot < ne_cap) {
+                ExpRec c;
+#pragma unroll
+                for (int j = 0; j < 9; j++) c.b[j] = 0;
+                c.b[0] = lo; c.b[1] = end;
+                c.level = cl; c.parent = begin + t; c.rank = my_rank;
+                c.same_start = (lo == s) ? same_start + nch : 0;
+                c.nch = 0; c.first_child = 0; c.id = 0;
+                rec[slot] = c;
+            } else {
+                atomicOr(&meta->overflow, TREE_OVERFLOW_EXPANDED);
+            }
+        }
+        __syncthreads();   // s_warp_tot / s_base are rewritten by the next round
     }
 }
 
-__global__ void __launch_bounds__(128) emit_kernel(ExpRec *__restrict__ rec, int begin, int count, int next_begin,
-                                                  const int *__restrict__ off, int max_leaf)
+// After the discovery and the scan of W: totals, overflow flags, box width and the walk's cell sizes.
+__global__ void tree_meta_kernel(TreeMeta *meta, const int *__restrict__ P, int n, const double *__restrict__ box, int ne_cap, int m_cap)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const ExpRec r = rec[begin + t];
-    const int l = r.level + 1;
-    if (l >= MAX_LEVEL) return;
-    int o = next_begin + off[t];
-    for (int k = 0; k < r.nch; k++) {
-        const int cs = r.b[k], ce = r.b[k + 1];
-        if (ce - cs > max_leaf) {
-            ExpRec c;
-            for (int j = 0; j < 9; j++) c.b[j] = 0;
-            c.b[0] = cs; c.b[1] = ce;
-            c.level = l; c.parent = begin + t; c.rank = k;
-            c.same_start = (cs == r.b[0]) ? r.same_start + r.nch : 0;
-            c.nch = 0; c.first_child = 0; c.id = 0;
-            rec[o++] = c;
-        }
+    if (threadIdx.x != 0) return;
+    int ne = 0, levels = 0;
+    for (int l = 0; l <= MAX_LEVEL; l++) {
+        const int cnt = meta->lvl_cnt[l];
+        if (cnt > 0) levels = l + 1;
+        ne += cnt;
+    }
+    if (ne > ne_cap) { atomicOr(&meta->overflow, TREE_OVERFLOW_EXPANDED); ne = ne_cap; }
+    const int M = 1 + P[n];
+    if (M > m_cap) atomicOr(&meta->overflow, TREE_OVERFLOW_NODES);
+    meta->num_expanded = ne;
+    meta->num_nodes = M;
+    meta->levels = levels;
+    const double w = box[3];
+    meta->box_width = w;
+    const double box_length = __dmul_rn(w, 2.0);                          // src/acceleration_barnes_hut.c:100
+    for (int level = 0; level <= MAX_LEVEL; level++) {
+        const double bl = __ddiv_rn(box_length, (double)(2 << level));    // :157
+        meta->cell2[level] = __dmul_rn(bl, bl);                            // :162 (left-hand side)
     }
 }
 
-// Numbering and node arrays in one pass over the expanded records.  first_child(u) = 1 + P[s_u] + same_start(u); the id of
-// u itself is first_child(parent) + rank (the parent's first_child is recomputed from the parent's record, so no kernel
-// boundary is needed).  A parent writes count / first position of all its children and the leaf defaults of the children
-// that stay leaves; an expanded child writes its own child count and first-child id (same rule as emit_kernel decides
-// who is expanded), so no entry has two writers.
-__global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *__restrict__ rec, int ne, int n, int max_leaf,
-                                                        const int *__restrict__ P, int *__restrict__ np,
-                                                        int *__restrict__ nchild, int *__restrict__ first, int *__restrict__ fc)
+// Numbering, topology and ropes in one pass over the expanded records, eight lanes per record (one per child).
+//   first_child(u) = 1 + P[s_u] + same_start(u);  id(u) = first_child(parent) + rank  -- both pure functions of the
+//   records' positions, so nothing here waits for another record's result.
+//   A parent writes first particle, level/count, rope and inclusion key of all its children and the leaf defaults of the
+//   children that stay leaves; an expanded node writes its own first-child id and child count; the moments kernel
+//   writes mass and centre of mass of expanded nodes later.  No field has two writers.
+//   Ropes: child k < nch-1 is followed by its next sibling (id + 1); the last child inherits its parent's rope, found by
+//   climbing while the node is itself a last child (1.3 steps on average); the root's rope ends the walk.
+//   Inclusion key: reference mode reproduces the walk's fetch keys[sorted_indices[first_particle]] -- the SORTED key
+//   array indexed by an ORIGINAL particle id (src/acceleration_barnes_hut.c:143-147); fixed mode uses the node's own key.
+__global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *__restrict__ rec, const TreeMeta *__restrict__ meta, int n, int max_leaf,
+                                                        const int *__restrict__ P, const long long *__restrict__ K,
+                                                        const int *__restrict__ perm, int fixed_mode,
+                                                        WalkGeo *__restrict__ geo, WalkTopo *__restrict__ topo)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= ne) return;
-    const ExpRec r = rec[u];
-    const int fcu = 1 + P[r.b[0]] + r.same_start;
-    int id = 0;
-    if (r.parent >= 0) {
-        const int ps = rec[r.parent].b[0], pss = rec[r.parent].same_start;
-        id = 1 + P[ps] + pss + r.rank;
-    } else {
-        np[0] = n; first[0] = 0;
-    }
-    rec[u].first_child = fcu;
-    rec[u].id = id;
-    nchild[id] = r.nch;
-    fc[id] = fcu;
-    const int l = r.level + 1;
-    for (int k = 0; k < r.nch; k++) {
-        const int cid = fcu + k, cnt = r.b[k + 1] - r.b[k];
-        np[cid] = cnt;
-        first[cid] = r.b[k];
-        if (!(cnt > max_leaf && l < MAX_LEVEL)) {
-            nchild[cid] = 0;
-            fc[cid] = -1;       // the reference leaves this uninitialised for leaves
+    if (meta->overflow) return;                      // ids would run past the planes; the host reports the flag
+    const int ne = meta->num_expanded;
+    for (int gt = blockIdx.x * blockDim.x + threadIdx.x; (gt >> 3) < ne; gt += gridDim.x * blockDim.x) {
+        const int u = gt >> 3, k = gt & 7;
+        const ExpRec r = rec[u];
+        const int fcu = 1 + P[r.b[0]] + r.same_start;
+        if (k == 0) {
+            int id = 0;
+            if (r.parent >= 0) {
+                const int ps = rec[r.parent].b[0], pss = rec[r.parent].same_start;
+                id = 1 + P[ps] + pss + r.rank;
+            } else {
+                topo[0].next = -1; topo[0].first = 0; topo[0].level_count = n;   // root: level 0
+                geo[0].kq = 0;
+            }
+            rec[u].first_child = fcu;
+            rec[u].id = id;
+            topo[id].fc = fcu;
+            topo[id].nch = r.nch;
+            topo[id].pad = 0;
         }
-    }
-}
-
-// Eight lanes per expanded node, one per child: the loads of the children's contributions (a leaf's particle through
-// perm -> posm, an expanded child's finished sums) go out together; then every lane of the octet adds the items up in
-// the reference's order (children in id order, the particles of a leaf one at a time), so the sums are bit-identical to
-// the serial loop.  Leaves with several particles (max_leaf > 1, or duplicates at level 21) are read in the ordered
-// phase by all eight lanes (same address: one transaction).
-__global__ void __launch_bounds__(128) moments_kernel(const ExpRec *__restrict__ rec, int begin, int count,
-                                                     const int *__restrict__ perm, const double4 *__restrict__ posm,
-                                                     const int *__restrict__ nchild, double *__restrict__ mass,
-                                                     double *__restrict__ mtd, double *__restrict__ cx,
-                                                     double *__restrict__ cy, double *__restrict__ cz)
-{
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = gt >> 3, o = gt & 7;
-    if (t >= count) return;                      // whole octets leave together
-    const ExpRec *r = rec + begin + t;
-    const int nch = r->nch, fcid = r->first_child;
-    const int g0 = (threadIdx.x & 31) & ~7;
-    const unsigned gmask = 0xffu << g0;
-    double im = 0.0, ix = 0.0, iy = 0.0, iz = 0.0;
-    int start = 0, cnt = 0, multi = 0;
-    if (o < nch) {
-        const int cid = fcid + o;
-        start = r->b[o];
-        cnt = r->b[o + 1] - start;
-        if (nchild[cid] != 0) {
-            im = mass[cid];
-            ix = mtd[3 * (size_t)cid + 0]; iy = mtd[3 * (size_t)cid + 1]; iz = mtd[3 * (size_t)cid + 2];
-        } else if (cnt == 1) {
-            const double4 q = posm[perm[start]];
-            im = q.w;
-            ix = __dmul_rn(q.w, q.x); iy = __dmul_rn(q.w, q.y); iz = __dmul_rn(q.w, q.z);
-        } else {
-            multi = 1;
-        }
-    }
-    double tot = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int k = 0; k < nch; k++) {
-        const int mk = __shfl_sync(gmask, multi, k, 8);
-        if (!mk) {
-            tot = __dadd_rn(tot, __shfl_sync(gmask, im, k, 8));
-            sx = __dadd_rn(sx, __shfl_sync(gmask, ix, k, 8));
-            sy = __dadd_rn(sy, __shfl_sync(gmask, iy, k, 8));
-            sz = __dadd_rn(sz, __shfl_sync(gmask, iz, k, 8));
-        } else {
-            const int ps = __shfl_sync(gmask, start, k, 8), pc = __shfl_sync(gmask, cnt, k, 8);
-            for (int p = ps; p < ps + pc; p++) {
-                const double4 q = posm[perm[p]];
-                tot = __dadd_rn(tot, q.w);
-                sx = __dadd_rn(sx, __dmul_rn(q.w, q.x));
-                sy = __dadd_rn(sy, __dmul_rn(q.w, q.y));
-                sz = __dadd_rn(sz, __dmul_rn(q.w, q.z));
+        if (k < r.nch) {
+            const int cid = fcu + k, first = r.b[k], cnt = r.b[k + 1] - first;
+            const int cl = r.level + 1;
+            int nxt = cid + 1;
+            if (k == r.nch - 1) {                     // last child: the rope of u
+                nxt = -1;
+                int v = u;
+                while (true) {
+                    const int parent = rec[v].parent;
+                    if (parent < 0) break;
+                    const int vr = rec[v].rank;
+                    if (vr < rec[parent].nch - 1) { nxt = 1 + P[rec[parent].b[0]] + rec[parent].same_start + vr + 1; break; }
+                    v = parent;
+                }
+            }
+            WalkTopo *w = topo + cid;
+            w->next = nxt;
+            w->first = first;
+            w->level_count = (cl << WALK_COUNT_BITS) | cnt;
+            geo[cid].kq = fixed_mode ? K[first] : K[perm[first]];
+            if (!(cnt > max_leaf && cl < MAX_LEVEL)) {   // stays a leaf
+                w->fc = -1; w->nch = 0; w->pad = 0;
+                w->mass = 0.0;
+                geo[cid].cx = 0.0; geo[cid].cy = 0.0; geo[cid].cz = 0.0;
             }
         }
     }
-    if (o == 0) {
-        const int id = r->id;
-        mass[id] = tot;
-        mtd[3 * (size_t)id + 0] = sx; mtd[3 * (size_t)id + 1] = sy; mtd[3 * (size_t)id + 2] = sz;
-        cx[id] = __ddiv_rn(sx, tot); cy[id] = __ddiv_rn(sy, tot); cz[id] = __ddiv_rn(sz, tot);
-    }
 }
 
-// Packed per-node record for the walk.  Reference mode reproduces the walk's key fetch
-// keys[sorted_indices[first_particle]] -- the SORTED key array indexed by an ORIGINAL particle id
-// (src/acceleration_barnes_hut.c:143-147); fixed mode uses the node's own first key.
-__global__ void __launch_bounds__(256) walk_nodes_kernel(int M, const int *__restrict__ np, const int *__restrict__ nchild,
-                                                        const int *__restrict__ first, const int *__restrict__ fc,
-                                                        const double *__restrict__ mass, const double *__restrict__ cx,
-                                                        const double *__restrict__ cy, const double *__restrict__ cz,
-                                                        const long long *__restrict__ K, const int *__restrict__ perm,
-                                                        int fixed_mode, WalkGeo *__restrict__ geo, WalkTopo *__restrict__ topo)
+// One level of the moments.  Eight lanes per expanded node, one per child: the loads of the children's contributions (a
+// leaf's particle from the Morton-sorted copy, an expanded child's finished sums) go out together; then every lane of
+// the octet adds the items up in the reference's order (children in id order, the particles of a leaf one at a time), so
+// the sums are bit-identical to the serial loop.  Leaves with several particles (max_leaf > 1, or duplicates at level
+// 21) are read in the ordered phase by all eight lanes (same address: one transaction).
+__global__ void __launch_bounds__(128) moments_kernel(const ExpRec *__restrict__ rec, const TreeMeta *__restrict__ meta, int l,
+                                                     int max_leaf, const double4 *__restrict__ psorted,
+                                                     WalkGeo *__restrict__ geo, WalkTopo *__restrict__ topo,
+                                                     double *__restrict__ mtd)
 {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= M) return;
-    WalkGeo *g = geo + id;
-    WalkTopo *w = topo + id;     // next / level are written by rope_kernel
-    const int f = first[id];
-    g->cx = cx[id]; g->cy = cy[id]; g->cz = cz[id];
-    g->kq = fixed_mode ? K[f] : K[perm[f]];
-    w->fc = nchild[id] > 0 ? fc[id] : -1;
-    w->first = f;
-    w->mass = mass[id];
-    w->pad = 0;
-    // next / level_count of every other node are written by rope_kernel (launched after this kernel)
-    if (id == 0) { w->next = -1; w->level_count = np[id]; }
+    if (meta->overflow) return;
+    const int begin = meta->lvl_off[l], count = meta->lvl_cnt[l];
+    const int o = threadIdx.x & 7;
+    const int g0 = (threadIdx.x & 31) & ~7;
+    const unsigned gmask = 0xffu << g0;
+    for (int gt = blockIdx.x * blockDim.x + threadIdx.x; (gt >> 3) < count; gt += gridDim.x * blockDim.x) {   // whole octets
+        const ExpRec *r = rec + begin + (gt >> 3);
+        const int nch = r->nch, fcid = r->first_child;
+        const bool child_level_expandable = (r->level + 1) < MAX_LEVEL;
+        double im = 0.0, ix = 0.0, iy = 0.0, iz = 0.0;
+        int start = 0, cnt = 0, multi = 0;
+        if (o < nch) {
+            const int cid = fcid + o;
+            start = r->b[o];
+            cnt = r->b[o + 1] - start;
+            if (cnt > max_leaf && child_level_expandable) {
+                im = topo[cid].mass;
+                ix = mtd[3 * (size_t)cid + 0]; iy = mtd[3 * (size_t)cid + 1]; iz = mtd[3 * (size_t)cid + 2];
+            } else if (cnt == 1) {
+                const double4 q = psorted[start];
+                im = q.w;
+                ix = __dmul_rn(q.w, q.x); iy = __dmul_rn(q.w, q.y); iz = __dmul_rn(q.w, q.z);
+            } else {
+                multi = 1;
+            }
+        }
+        double tot = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int k = 0; k < nch; k++) {
+            const int mk = __shfl_sync(gmask, multi, k, 8);
+            if (!mk) {
+                tot = __dadd_rn(tot, __shfl_sync(gmask, im, k, 8));
+                sx = __dadd_rn(sx, __shfl_sync(gmask, ix, k, 8));
+                sy = __dadd_rn(sy, __shfl_sync(gmask, iy, k, 8));
+                sz = __dadd_rn(sz, __shfl_sync(gmask, iz, k, 8));
+            } else {
+                const int ps = __shfl_sync(gmask, start, k, 8), pc = __shfl_sync(gmask, cnt, k, 8);
+                for (int p = ps; p < ps + pc; p++) {
+                    const double4 q = psorted[p];
+                    tot = __dadd_rn(tot, q.w);
+                    sx = __dadd_rn(sx, __dmul_rn(q.w, q.x));
+                    sy = __dadd_rn(sy, __dmul_rn(q.w, q.y));
+                    sz = __dadd_rn(sz, __dmul_rn(q.w, q.z));
+                }
+            }
+        }
+        if (o == 0) {
+            const int id = r->id;
+            topo[id].mass = tot;
+            mtd[3 * (size_t)id + 0] = sx; mtd[3 * (size_t)id + 1] = sy; mtd[3 * (size_t)id + 2] = sz;
+            geo[id].cx = __ddiv_rn(sx, tot); geo[id].cy = __ddiv_rn(sy, tot); geo[id].cz = __ddiv_rn(sz, tot);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const double4 *__restrict__ posm, const int *__restrict__ perm, int n,
@@ -248,52 +318,34 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const double4 *__res
     if (p < n) out[p] = posm[perm[p]];
 }
 
-// Ropes in one launch: child k < nch-1 is followed by its next sibling (id + 1); the last child inherits its parent's
-// rope, found by climbing while the node is itself a last child (1.3 steps on average); the root's rope ends the walk.
-__global__ void __launch_bounds__(256) rope_kernel(const ExpRec *__restrict__ rec, int ne, WalkTopo *__restrict__ nodes)
+// construct_octree() only: the eight per-node arrays of LinearOctree from the walk planes.
+__global__ void __launch_bounds__(256) export_nodes_kernel(int M, const WalkGeo *__restrict__ geo, const WalkTopo *__restrict__ topo,
+                                                          int *__restrict__ np, int *__restrict__ nchild, int *__restrict__ first,
+                                                          int *__restrict__ fc, double *__restrict__ mass, double *__restrict__ cx,
+                                                          double *__restrict__ cy, double *__restrict__ cz)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= ne) return;
-    const ExpRec r = rec[u];
-    int my_next = -1;
-    int v = u;
-    while (true) {
-        const int parent = rec[v].parent;
-        if (parent < 0) break;                                   // reached the root: -1
-        if (rec[v].rank < rec[parent].nch - 1) { my_next = rec[v].id + 1; break; }
-        v = parent;
-    }
-    for (int k = 0; k < r.nch; k++) {
-        const int cid = r.first_child + k;
-        nodes[cid].next = (k < r.nch - 1) ? cid + 1 : my_next;
-        nodes[cid].level_count = ((r.level + 1) << WALK_COUNT_BITS) | (r.b[k + 1] - r.b[k]);
-    }
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= M) return;
+    const WalkTopo w = topo[id];
+    const WalkGeo g = geo[id];
+    np[id] = w.level_count & COUNT_MASK;
+    nchild[id] = w.nch;
+    first[id] = w.first;
+    fc[id] = w.fc;              // -1 for leaves (the reference leaves it uninitialised)
+    mass[id] = w.mass;
+    cx[id] = g.cx; cy[id] = g.cy; cz[id] = g.cz;
 }
 
-static int grow_preserve(grav_b200_ctx *c, DevBuf &buf, size_t used_bytes, size_t need_bytes)
+static int grid_for(long long threads_needed, int block, int max_blocks)
 {
-    if (need_bytes <= buf.cap && buf.p) return GRAV_B200_OK;
-    size_t want = need_bytes + need_bytes / 2;
-    void *np = nullptr;
-    cudaError_t e = cudaMalloc(&np, want);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        want = need_bytes;
-        e = cudaMalloc(&np, want);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
-    }
-    if (buf.p && used_bytes) {
-        e = cudaMemcpyAsync(np, buf.p, used_bytes, cudaMemcpyDeviceToDevice, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) { cudaFree(np); return cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__); }
-    }
-    if (buf.p) cudaFree(buf.p);
-    buf.p = np;
-    buf.cap = want;
-    return GRAV_B200_OK;
+    long long b = (threads_needed + block - 1) / block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
 }
 
-// Builds keys, permutation, node arrays and moments on the device.  Leaves c->tree ready for bh_walk().
+// Builds keys, permutation, walk planes and moments on the device.  Leaves c->tree ready for bh_walk().
+// Queues work only: no host synchronisation (see the header comment).
 int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double box_width)
 {
     DevTree &t = c->tree;
@@ -307,112 +359,96 @@ int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double bo
 
     stage_begin(c, ST_BUILD);
     const long long *K = t.keys.as<long long>();
+    // capacities: typical trees have 0.48 n expanded nodes and 1.48 n nodes; leaves are disjoint and non-empty, so
+    // nodes <= 1 + n + expanded holds for any tree
+    const long long ne_cap = (2LL * n + 1024) * t.slack, m_cap = ne_cap + n + 1;
+    if (m_cap >= (1LL << 28)) { set_error("tree capacity %lld exceeds the 2^28 nodes a walk-stack entry can address", m_cap); return GRAV_B200_EINVAL; }
+    t.ne_cap = (int)ne_cap;
+    t.m_cap = (int)m_cap;
     GB_TRY(t.wsum.reserve(sizeof(int) * ((size_t)n + 1)));
     GB_TRY(t.wscan.reserve(sizeof(int) * ((size_t)n + 1)));
+    GB_TRY(t.exp_rec.reserve(sizeof(ExpRec) * (size_t)ne_cap));
+    GB_TRY(t.meta.reserve(sizeof(TreeMeta)));
+    GB_TRY(t.node_walk.reserve((sizeof(WalkGeo) + sizeof(WalkTopo)) * (size_t)m_cap));
+    GB_TRY(t.node_mtd.reserve(sizeof(double) * 3 * (size_t)m_cap));
+    GB_TRY(t.posm_sorted.reserve(sizeof(double4) * (size_t)n));
+    if (!t.h_meta) GB_CUDA(cudaHostAlloc((void **)&t.h_meta, sizeof(TreeMeta), cudaHostAllocDefault));
+    ExpRec *rec = t.exp_rec.as<ExpRec>();
+    TreeMeta *meta = t.meta.as<TreeMeta>();
+    WalkGeo *geo = t.geo();
+    WalkTopo *topo = t.topo();
+    const int max_blocks = c->sm_count * 8;
+
     GB_CUDA(cudaMemsetAsync(t.wsum.p, 0, sizeof(int) * ((size_t)n + 1), c->stream));
-    // a generous first guess for the record count; grown on demand (deep chains can exceed it)
-    GB_TRY(grow_preserve(c, t.exp_rec, 0, sizeof(ExpRec) * ((size_t)n / 2 + 1024)));
-    root_init_kernel<<<1, 1, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), n);
+    tree_init_kernel<<<1, 32, 0, c->stream>>>(rec, meta, n);
     GB_LAUNCH_CHECK();
-    count_launch();
+    gather_sorted_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->posm.as<double4>(), t.perm.as<int>(), n, t.posm_sorted.as<double4>());
+    GB_LAUNCH_CHECK();
+    count_launch(2);
 
-    int level_off[MAX_LEVEL + 2];
-    level_off[0] = 0;
-    level_off[1] = 1;
-    int levels = 1;   // number of levels holding expanded nodes
+    // discovery: level l holds at most min(8^l, n / (max_leaf + 1)) expanded nodes
+    const long long most = (long long)n / (max_leaf + 1) + 1;
+    long long pow8 = 1;
     for (int l = 0; l < MAX_LEVEL; l++) {
-        const int begin = level_off[l], count = level_off[l + 1] - begin;
-        GB_TRY(t.counters.reserve(sizeof(int) * ((size_t)count + 1)));
-        int *nexp = t.counters.as<int>();
-        expand_kernel<<<(8 * (count + 1) + 127) / 128, 128, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, K, max_leaf,
-                                                                     t.wsum.as<int>(), nexp);
+        const long long ub = pow8 < most ? pow8 : most;
+        expand_kernel<<<grid_for(ub * 8, EXPAND_THREADS, max_blocks), EXPAND_THREADS, 0, c->stream>>>(rec, meta, l, K, max_leaf,
+                                                                                                     t.wsum.as<int>(), t.ne_cap);
         GB_LAUNCH_CHECK();
         count_launch();
-        if (l + 1 >= MAX_LEVEL) { levels = l + 1; break; }   // level-21 nodes are never expanded
-        GB_TRY(exclusive_scan_int(c, nexp, nexp, count + 1, t.scan_tmp));
-        int total = 0;
-        GB_CUDA(cudaMemcpyAsync(&total, nexp + count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        GB_CUDA(cudaStreamSynchronize(c->stream));
-        levels = l + 1;
-        if (total == 0) break;
-        const size_t used = sizeof(ExpRec) * (size_t)level_off[l + 1];
-        GB_TRY(grow_preserve(c, t.exp_rec, used, used + sizeof(ExpRec) * (size_t)total));
-        emit_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), begin, count, level_off[l + 1], nexp,
-                                                               max_leaf);
-        GB_LAUNCH_CHECK();
-        count_launch();
-        level_off[l + 2] = level_off[l + 1] + total;
+        if (pow8 < most) pow8 *= 8;
     }
-    const int ne = level_off[levels];
-    t.num_expanded = ne;
-    t.max_level = levels;
-    for (int l = 0; l <= levels; l++) t.level_off[l] = level_off[l];
-
     // numbering
     GB_TRY(exclusive_scan_int(c, t.wsum.as<int>(), t.wscan.as<int>(), n + 1, t.scan_tmp));
-    int total_children = 0;
-    GB_CUDA(cudaMemcpyAsync(&total_children, t.wscan.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    GB_CUDA(cudaMemcpyAsync(&t.box_width, t.bbox.as<double>() + 8 + 3, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    GB_CUDA(cudaStreamSynchronize(c->stream));
-    const int M = 1 + total_children;
-    t.num_nodes = M;
-    const size_t mi = sizeof(int) * (size_t)M, md = sizeof(double) * (size_t)M;
-    GB_TRY(t.node_np.reserve(mi));
-    GB_TRY(t.node_nch.reserve(mi));
-    GB_TRY(t.node_first.reserve(mi));
-    GB_TRY(t.node_fc.reserve(mi));
-    GB_TRY(t.node_mass.reserve(md));
-    GB_TRY(t.node_cx.reserve(md));
-    GB_TRY(t.node_cy.reserve(md));
-    GB_TRY(t.node_cz.reserve(md));
-    GB_TRY(t.node_mtd.reserve(3 * md));
-    GB_CUDA(cudaMemsetAsync(t.node_mass.p, 0, md, c->stream));
-    GB_CUDA(cudaMemsetAsync(t.node_cx.p, 0, md, c->stream));
-    GB_CUDA(cudaMemsetAsync(t.node_cy.p, 0, md, c->stream));
-    GB_CUDA(cudaMemsetAsync(t.node_cz.p, 0, md, c->stream));
-    ExpRec *rec = t.exp_rec.as<ExpRec>();
-    const int eb = (ne + 255) / 256;
-    fill_nodes_kernel<<<eb, 256, 0, c->stream>>>(rec, ne, n, max_leaf, t.wscan.as<int>(), t.node_np.as<int>(), t.node_nch.as<int>(),
-                                                t.node_first.as<int>(), t.node_fc.as<int>());
+    tree_meta_kernel<<<1, 32, 0, c->stream>>>(meta, t.wscan.as<int>(), n, t.bbox.as<double>() + 8, t.ne_cap, t.m_cap);
     GB_LAUNCH_CHECK();
-    count_launch();
-
+    fill_nodes_kernel<<<grid_for(most * 8, 256, max_blocks * 2), 256, 0, c->stream>>>(rec, meta, n, max_leaf, t.wscan.as<int>(), K,
+                                                                                     t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0,
+                                                                                     geo, topo);
+    GB_LAUNCH_CHECK();
+    count_launch(2);
     // moments, deepest level first
-    for (int l = levels - 1; l >= 0; l--) {
-        const int begin = level_off[l], count = level_off[l + 1] - begin;
-        if (count <= 0) continue;
-        moments_kernel<<<(8 * count + 127) / 128, 128, 0, c->stream>>>(rec, begin, count, t.perm.as<int>(), c->posm.as<double4>(),
-                                                                  t.node_nch.as<int>(), t.node_mass.as<double>(),
-                                                                  t.node_mtd.as<double>(), t.node_cx.as<double>(),
-                                                                  t.node_cy.as<double>(), t.node_cz.as<double>());
+    pow8 = 1;
+    long long ubs[MAX_LEVEL];
+    for (int l = 0; l < MAX_LEVEL; l++) { ubs[l] = pow8 < most ? pow8 : most; if (pow8 < most) pow8 *= 8; }
+    for (int l = MAX_LEVEL - 1; l >= 0; l--) {
+        moments_kernel<<<grid_for(ubs[l] * 8, 128, max_blocks * 2), 128, 0, c->stream>>>(rec, meta, l, max_leaf, t.posm_sorted.as<double4>(),
+                                                                                        geo, topo, t.node_mtd.as<double>());
         GB_LAUNCH_CHECK();
         count_launch();
     }
+    GB_CUDA(cudaMemcpyAsync(t.h_meta, meta, sizeof(TreeMeta), cudaMemcpyDeviceToHost, c->stream));
+    t.built = true;
     stage_end(c, ST_BUILD);
     return GRAV_B200_OK;
 }
 
-int bh_pack_walk_nodes(grav_b200_ctx *c)
+// To be called after the stream has been synchronised: reports a build that did not fit its buffers.
+int bh_check(grav_b200_ctx *c)
 {
     DevTree &t = c->tree;
-    const int M = t.num_nodes;
-    GB_TRY(t.node_walk.reserve((sizeof(WalkGeo) + sizeof(WalkTopo)) * (size_t)M));
-    WalkGeo *geo = t.node_walk.as<WalkGeo>();
-    WalkTopo *nodes = reinterpret_cast<WalkTopo *>(geo + M);   // second plane
-    walk_nodes_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(M, t.node_np.as<int>(), t.node_nch.as<int>(), t.node_first.as<int>(),
-                                                            t.node_fc.as<int>(), t.node_mass.as<double>(), t.node_cx.as<double>(),
-                                                            t.node_cy.as<double>(), t.node_cz.as<double>(), t.keys.as<long long>(),
-                                                            t.perm.as<int>(), c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0, geo, nodes);
-    GB_LAUNCH_CHECK();
-    count_launch();
-    GB_TRY(t.posm_sorted.reserve(sizeof(double4) * (size_t)t.n));
-    gather_sorted_kernel<<<(t.n + 255) / 256, 256, 0, c->stream>>>(c->posm.as<double4>(), t.perm.as<int>(), t.n, t.posm_sorted.as<double4>());
-    GB_LAUNCH_CHECK();
-    count_launch();
-    rope_kernel<<<(t.num_expanded + 255) / 256, 256, 0, c->stream>>>(t.exp_rec.as<ExpRec>(), t.num_expanded, nodes);
-    GB_LAUNCH_CHECK();
-    count_launch();
+    if (!t.built || !t.h_meta) return GRAV_B200_OK;
+    t.built = false;
+    if (t.h_meta->overflow) {
+        set_error("the octree needs more room than was reserved (%d expanded nodes / %d nodes for n = %d; flags %d): "
+                  "deep chains of close particles.  The host-pointer entries retry by themselves; for a resident run raise "
+                  "GRAV_B200_TREE_SLACK (currently %d)", t.ne_cap, t.m_cap, t.n, t.h_meta->overflow, t.slack);
+        return GRAV_B200_ETREE;
+    }
     return GRAV_B200_OK;
+}
+
+// Build, wait, and if the tree did not fit rebuild with more room (the positions are still resident).  For callers
+// that synchronise anyway: construct_octree(), the first force evaluation of a resident integration.
+int bh_build_checked(grav_b200_ctx *c, int max_leaf, const double *box_center, double box_width)
+{
+    for (;;) {
+        GB_TRY(bh_build(c, max_leaf, box_center, box_width));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        const int rc = bh_check(c);
+        if (rc != GRAV_B200_ETREE) return rc;
+        if (c->tree.slack >= 16) return rc;   // 32 n records cover the worst case of 21 levels x n / 2 nodes
+        c->tree.slack *= 2;
+    }
 }
 
 }  // namespace gb
@@ -452,22 +488,34 @@ extern "C" int grav_b200_construct_octree(int n, const double *x, const double *
     grav_b200_ctx *c;
     GB_TRY(default_ctx_locked_begin(&c));
     int rc = grav_b200_ctx_set_system(c, n, x, nullptr, m, 1.0);
-    if (rc == GRAV_B200_OK) rc = bh_build(c, max_leaf, box_center, box_width);
+    if (rc == GRAV_B200_OK) rc = bh_build_checked(c, max_leaf, box_center, box_width);
     if (rc == GRAV_B200_OK) {
         DevTree &t = c->tree;
-        const size_t M = (size_t)t.num_nodes;
-        *out_box_width = t.box_width;
-        *out_num_nodes = t.num_nodes;
-        rc = copy_out(c, keys, t.keys.p, (size_t)n);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, sorted_indices, t.perm.p, (size_t)n);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_num_particles, t.node_np.p, M);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_num_internal_children, t.node_nch.p, M);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_first_particle_sorted_idx, t.node_first.p, M);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_first_internal_children_idx, t.node_fc.p, M);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_mass, t.node_mass.p, M);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_x, t.node_cx.p, M);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_y, t.node_cy.p, M);
-        if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_z, t.node_cz.p, M);
+        const size_t M = (size_t)t.h_meta->num_nodes;
+        *out_box_width = t.h_meta->box_width;
+        *out_num_nodes = (int)M;
+        // the LinearOctree arrays are not part of the hot path any more: derive them from the walk planes
+        const size_t Mp = (M + 1) & ~(size_t)1;                      // keeps the double arrays 8-byte aligned
+        rc = t.xport.reserve((4 * sizeof(int) + 4 * sizeof(double)) * Mp);
+        if (rc == GRAV_B200_OK) {
+            int *xi = t.xport.as<int>();
+            double *xd = reinterpret_cast<double *>(xi + 4 * Mp);
+            export_nodes_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>((int)M, t.geo(), t.topo(), xi, xi + Mp, xi + 2 * Mp,
+                                                                                  xi + 3 * Mp, xd, xd + Mp, xd + 2 * Mp, xd + 3 * Mp);
+            cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) rc = cuda_fail(le, "export_nodes_kernel", __FILE__, __LINE__);
+            count_launch();
+            if (rc == GRAV_B200_OK) rc = copy_out(c, keys, t.keys.p, (size_t)n);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, sorted_indices, t.perm.p, (size_t)n);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_num_particles, xi, M);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_num_internal_children, xi + Mp, M);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_first_particle_sorted_idx, xi + 2 * Mp, M);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_first_internal_children_idx, xi + 3 * Mp, M);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_mass, xd, M);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_x, xd + Mp, M);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_y, xd + 2 * Mp, M);
+            if (rc == GRAV_B200_OK) rc = copy_out(c, tree_com_z, xd + 3 * Mp, M);
+        }
         if (rc == GRAV_B200_OK) {
             cudaError_t e = cudaStreamSynchronize(c->stream);
             if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);

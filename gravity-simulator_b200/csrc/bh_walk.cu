@@ -3,24 +3,26 @@
 // Reference: helper_compute_acceleration (src/acceleration_barnes_hut.c:78-248): one CPU thread per particle
 // (in Morton order) runs a depth-first walk with a private 22-frame stack.
 //
-// Here: one GPU thread per target, targets taken in Morton order so the 32 lanes of a warp follow nearly the
-// same path (their node loads then hit the same sectors), and the walk is STACKLESS: every node record carries
-// a rope (`next`, the node that follows in depth-first order when the subtree is skipped), so a visit is
-//     accept or leaf  ->  node = next          open  ->  node = first child
-// and each lane advances through exactly the nodes, in exactly the order, the reference visits for that
-// particle.  History (ncu evidence under profiles/):
-//   r1_walk_warp_union        one traversal per warp with lane masks: issue-bound, 7/32 lanes in the accept
-//                             path, 4.4x the node visits one particle needs                     67.5 ms
-//   r1_walk_stackless_exact   independent lanes + ropes: half the executed instructions          41.7 ms
-//   r1_walk_state_machine     one item per trip; still ran a 3-load leaf path for 2/32 lanes in 77 % of trips
-//   (this version)            accepted nodes and leaf particles share ONE source path: a source is a packed
-//                             (x,y,z,m) record -- the node's (com, mass) or the particle's record from a
-//                             Morton-sorted copy -- so the self test is a position compare and no lane waits
-//                             on a perm -> posm chain                                   (N=2^20 Plummer, 1 GPU)
+// Two kernels, same visit set (every accept / open / leaf decision is taken per target with IEEE operations without FMA
+// contraction, in the reference's operation order -- a flipped decision would change a force at the 1e-3 level):
 //
-// All arithmetic that feeds a decision or the result uses IEEE operations without FMA contraction
-// (__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn) in the reference's order, so in reference mode the output is
-// bit-identical to the x86-64 reference build.
+//   walk_coop_kernel   DEFAULT.  One WARP per target, shared-memory stack of nodes to open.  Per trip the warp pops up to
+//                      four opened nodes; the 8 lanes of an octet take the (<= 8, contiguous) children of one of them:
+//                      coalesced record loads, the opening test in parallel, accepted nodes and single-particle leaves
+//                      evaluated at once into lane-private partial sums (m r^-3 from the direct sum's rsqrt seed + one
+//                      correction, FMAs), opened children pushed with a ballot.  The partial sums are added across the
+//                      warp at the end, so the SUMMATION ORDER differs from the reference: results agree to ~1e-15
+//                      relative (tests gate at 1e-12, the north-star tolerance).  Idle lanes are the price of the
+//                      cooperative scheme (6.7-7.1 of 8 children per opened node, measured with the oracle), but there is
+//                      no per-lane state machine, no divergent traversal, and the loads of a trip are 2-3 lines per octet.
+//   walk_kernel        GRAV_B200_BH_EXACT=1 (or grav_b200_set_bh_exact).  One THREAD per target, stackless via ropes,
+//                      one item (node visit or leaf particle) per loop trip, sources in the reference's depth-first order
+//                      with sqrt / div / separate multiplies: output bit-identical to the x86-64 reference build.
+//                      Round-1 history of this kernel (ncu evidence under profiles/r1_walk_*): one traversal per warp
+//                      with lane masks 67.5 ms -> independent lanes + ropes 41.7 -> one item per trip 39.2 -> 256-bit
+//                      loads and two 32-byte record planes 30.8 ms (N = 2^20 Plummer, theta = 0.5, one GPU).
+//                      Its <FIXED, false> instantiation (GRAV_B200_WALK_KERNEL=lane) keeps the per-lane traversal but
+//                      uses the fast evaluation: the A/B point between the two designs.
 //
 // Modes (grav_b200_set_bh_mode):
 //   reference  bug-for-bug: the inclusion test compares keys fetched from the SORTED key array with ORIGINAL
@@ -32,16 +34,11 @@
 namespace gb {
 
 constexpr int MAX_LEVEL = 21;
+constexpr int COUNT_MASK = (1 << WALK_COUNT_BITS) - 1;
 constexpr int WALK_BLOCK = 128;
-constexpr int WALK_CHUNK = 2048;    // multi-GPU: granularity of the interleaved target partition (16 CTAs)
-// Tuning knobs kept for A/B builds (measured at N=2^20 Plummer, reference mode):
-//   WALK_VARIANT 0  next node's record prefetched into registers before the arithmetic        39.3 ms  <- default
-//   WALK_VARIANT 1  prefetch.global.L1 + reload at loop top (12 fewer live registers)          41.9 ms
+constexpr int WALK_CHUNK = 2048;    // multi-GPU: granularity of the interleaved target partition
+// Tuning knobs of the per-lane kernel kept for A/B builds (measured at N=2^20 Plummer, reference mode, round 1):
 //   WALK_MINB 10/12 (48/40 registers, more resident warps)                                41.6 / 50.7 ms
-// More occupancy does not help: the kernel is bound by instructions per item and lane divergence, not latency.
-#ifndef WALK_VARIANT
-#define WALK_VARIANT 0
-#endif
 #ifndef WALK_MINB
 #define WALK_MINB 8
 #endif
@@ -49,62 +46,204 @@ constexpr int WALK_CHUNK = 2048;    // multi-GPU: granularity of the interleaved
 struct WalkArgs {
     const WalkGeo *geo;        // plane 0: com + key
     const WalkTopo *topo;      // plane 1: topology + mass
+    const TreeMeta *meta;      // device-side build bookkeeping: overflow flag, cell sizes
     const long long *K;        // sorted keys
     const int *perm;           // sorted position -> particle id
     const double4 *psorted;    // particle records in sorted order
-    const int *tord;           // optional: thread q handles sorted position tord[q] (walk-key grouping), else q
-    int p_lo, p_hi;            // sorted positions (or slots of tord) handled by this launch
-    int chunk, rank, world;    // world > 1: the launch covers chunks rank, rank + world, ... of `chunk` consecutive slots
+    const int *tord;           // optional (per-lane kernel): slot q handles sorted position tord[q] (walk-key grouping)
+    int n;                     // sorted positions are [0, n)
+    int chunk, rank, world;    // world > 1: this rank's slot t is position ((t / chunk) * world + rank) * chunk + t % chunk
     double G, eps2, theta2;
-    double cell2[MAX_LEVEL + 2];   // (box_length / (2 << level))^2 per child level
-    double *acc;               // AoS [3n] by particle id
+    double *acc;               // AoS [3n] by particle id (world == 1)
+    double *out_slots;         // world > 1: results in slot order, [3 * slots]
 };
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// 256-bit read-only global load (sm_100: LDG.E.ENL2.256).  The walk is bound by L1 data-pipe wavefronts
-// (l1tex__data_pipe_lsu_wavefronts 78 % of peak, profiles/r1_walk_state_machine_n256k.txt): every load instruction
-// of a warp costs one wavefront per distinct 128-byte line its lanes touch, so a node visit is served by TWO load
-// instructions (32 + 16 bytes) instead of three, and a particle record by ONE instead of two.
+// 256-bit read-only global load (sm_100: LDG.E.ENL2.256).  Every load instruction of a warp costs one L1 wavefront per
+// distinct 128-byte line its lanes touch, so a node visit is served by TWO load instructions (geo + topo plane) and a
+// particle record by ONE.
 __device__ __forceinline__ void ldg256(const void *p, long long &a, long long &b, long long &c, long long &d)
 {
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
-struct NodeRec {   // a whole WalkNode as two 256-bit loads (the mass rides along: no third load on accept)
+struct NodeRec {   // a node's two records as two 256-bit loads (the mass rides along: no third load on accept)
     long long cx, cy, cz, kq;   // raw bits
-    long long fc_next, first_lc, mass, pad;
+    long long fc_next, first_lc, mass, nch_pad;
 };
 __device__ __forceinline__ NodeRec load_rec(const WalkGeo *geo, const WalkTopo *topo, int node)
 {
     NodeRec r;
     ldg256(geo + node, r.cx, r.cy, r.cz, r.kq);
-    ldg256(topo + node, r.fc_next, r.first_lc, r.mass, r.pad);
+    ldg256(topo + node, r.fc_next, r.first_lc, r.mass, r.nch_pad);
     return r;
 }
 
+__device__ __forceinline__ long long slot_to_position(const WalkArgs &a, long long t)
+{
+    // interleaved chunks: walk cost varies smoothly along the Morton curve (dense centre vs halo), so every rank
+    // gets a sample of all regions instead of one contiguous stretch
+    return a.world > 1 ? ((t / a.chunk) * a.world + a.rank) * a.chunk + t % a.chunk : t;
+}
+
+// fast evaluation of one source: the direct sum's 16 FP64 instructions; the sums carry G-less
+// "source minus target" terms, G is applied once at the end
+__device__ __forceinline__ void eval_fast(double sx, double sy, double sz, double sm, double xi, double yi, double zi,
+                                          double eps2, double &ax, double &ay, double &az)
+{
+    const double dx = sx - xi, dy = sy - yi, dz = sz - zi;
+    double r2 = fma(dx, dx, eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    const double s = inv_r3_times_m(r2, sm);
+    ax = fma(s, dx, ax);
+    ay = fma(s, dy, ay);
+    az = fma(s, dz, az);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// warp-cooperative walk
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CW_WARPS = 4;       // warps per CTA
+constexpr int CW_STACK = 512;     // stack entries per warp (4 bytes each: first child id << 4 | number of children)
+// Above CW_HIGH entries the warp pops ONE opened node per trip, i.e. walks depth-first, where the stack grows by at most
+// 7 entries per level, 140 in all; four at a time it grows by at most 28 per trip.  320 + 28 + 140 < 512.
+constexpr int CW_HIGH = 320;
+
+template <bool FIXED>
+__global__ void __launch_bounds__(CW_WARPS * 32, 8) walk_coop_kernel(const WalkArgs a, int tpw, long long slots)
+{
+    __shared__ double s_cell2[MAX_LEVEL + 3];
+    __shared__ unsigned s_stack[CW_WARPS][CW_STACK];
+    if (threadIdx.x < MAX_LEVEL + 1) s_cell2[threadIdx.x] = a.meta->cell2[threadIdx.x];
+    __syncthreads();
+    if (a.meta->overflow) return;   // the build did not fit its buffers: the planes are not a tree (reported by the host)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned *stk = s_stack[wib];
+    const int e = lane >> 3, k = lane & 7;
+    const unsigned lt = (1u << lane) - 1u;
+    const int root_fc = __ldg(&a.topo[0].fc), root_nch = __ldg(&a.topo[0].nch);   // the root is always expanded
+    const long long t0 = ((long long)blockIdx.x * CW_WARPS + wib) * tpw;
+    for (int tt = 0; tt < tpw; tt++) {
+        const long long t = t0 + tt;                     // slot of this rank
+        if (t >= slots) break;
+        const long long q = slot_to_position(a, t);
+        if (q >= a.n) break;                             // positions grow with the slot
+        const int p = (int)q;
+        const int idx = __ldg(&a.perm[p]);
+        long long mx, my, mz, mw;
+        ldg256(a.psorted + p, mx, my, mz, mw);
+        const double xi = __longlong_as_double(mx), yi = __longlong_as_double(my), zi = __longlong_as_double(mz);
+        const long long ki = FIXED ? __ldg(&a.K[p]) : __ldg(&a.K[idx]);
+        double ax = 0.0, ay = 0.0, az = 0.0;
+
+        int sp = 0;
+        int fc = (e == 0) ? root_fc : 0;
+        int nch = (e == 0) ? root_nch : 0;
+        bool active = k < nch;
+        NodeRec rec = {};
+        if (active) rec = load_rec(a.geo, a.topo, fc + k);
+        for (;;) {
+            bool open = false, have = false;
+            int lf_first = 0, lf_count = 0;
+            double sx = 0.0, sy = 0.0, sz = 0.0, sm = 0.0;
+            unsigned child_ent = 0;
+            if (active) {
+                const double cx = __longlong_as_double(rec.cx), cy = __longlong_as_double(rec.cy), cz = __longlong_as_double(rec.cz);
+                const int cfc = (int)rec.fc_next;
+                const int lc = (int)(rec.first_lc >> 32);
+                const int level = lc >> WALK_COUNT_BITS;
+                const bool leaf = cfc < 0;
+                const bool inside = ((ki ^ rec.kq) >> (3 * (MAX_LEVEL - level))) == 0;
+                // the decision arithmetic of src/acceleration_barnes_hut.c:150-162, operation for operation
+                const double rx = __dsub_rn(xi, cx), ry = __dsub_rn(yi, cy), rz = __dsub_rn(zi, cz);
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                const bool far = s_cell2[level] < __dmul_rn(a.theta2, d2);
+                const bool accepted = FIXED ? (!inside && !leaf && far) : (!inside && far);
+                if (accepted) {
+                    sm = __longlong_as_double(rec.mass);
+                    have = sm != 0.0;             // d2 > 0 here, so a zero-mass node (a dropped leaf) contributes exactly 0
+                    sx = cx; sy = cy; sz = cz;
+                } else if (leaf) {
+                    lf_first = (int)rec.first_lc;
+                    lf_count = lc & COUNT_MASK;
+                } else {
+                    open = true;
+                    child_ent = ((unsigned)cfc << 4) | (unsigned)(int)rec.nch_pad;
+                }
+            }
+            if (lf_count > 0 && lf_first != p) {      // first (usually only) particle of a leaf: same path as an accepted node
+                long long qx, qy, qz, qw;
+                ldg256(a.psorted + lf_first, qx, qy, qz, qw);
+                sx = __longlong_as_double(qx); sy = __longlong_as_double(qy); sz = __longlong_as_double(qz);
+                sm = __longlong_as_double(qw);
+                have = true;
+            }
+            const unsigned om = __ballot_sync(0xffffffffu, open);
+            if (open) stk[sp + __popc(om & lt)] = child_ent;
+            sp += __popc(om);
+            __syncwarp();
+            // next batch: its record loads are in flight while this trip's sources are evaluated
+            const bool more = sp > 0;
+            if (more) {
+                const int take = sp > CW_HIGH ? 1 : min(sp, 4);
+                const unsigned ent = (e < take) ? stk[sp - 1 - e] : 0u;
+                __syncwarp();
+                sp -= take;
+                fc = (int)(ent >> 4);
+                nch = (int)(ent & 15u);
+                active = k < nch;
+                if (active) rec = load_rec(a.geo, a.topo, fc + k);
+            }
+            if (have) eval_fast(sx, sy, sz, sm, xi, yi, zi, a.eps2, ax, ay, az);
+            if (lf_count > 1) {                       // max_leaf > 1, or duplicates at level 21: the rest of the leaf
+                for (int j = 1; j < lf_count; j++) {
+                    const int pos = lf_first + j;
+                    if (pos == p) continue;
+                    long long qx, qy, qz, qw;
+                    ldg256(a.psorted + pos, qx, qy, qz, qw);
+                    eval_fast(__longlong_as_double(qx), __longlong_as_double(qy), __longlong_as_double(qz), __longlong_as_double(qw),
+                              xi, yi, zi, a.eps2, ax, ay, az);
+                }
+            }
+            if (!more) break;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ax += __shfl_xor_sync(0xffffffffu, ax, d);
+            ay += __shfl_xor_sync(0xffffffffu, ay, d);
+            az += __shfl_xor_sync(0xffffffffu, az, d);
+        }
+        if (lane < 3) {
+            const double v = a.G * (lane == 0 ? ax : (lane == 1 ? ay : az));
+            if (a.out_slots) a.out_slots[3 * (size_t)t + lane] = v;
+            else a.acc[3 * (size_t)idx + lane] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-lane walk (bit-exact mode, and the fast-evaluation A/B variant)
+// ---------------------------------------------------------------------------------------------------------------------
 // Per-lane state machine.  Each trip of the loop handles ONE item for the lane -- a node visit, or the next
 // particle of a leaf that is being summed directly -- in steps that are the same code for every lane:
 //   decide    opening test on the current node record -> the next node id, and whether there is a source
 //   fetch     the next node's record is requested BEFORE the arithmetic below (its latency overlaps the sqrt/div);
 //             the source's mass (accepted node) or record (leaf particle) is loaded
-//   evaluate  R = x_i - x_src, f = G m / r^3 and the three accumulator updates: sqrt(((rx^2+ry^2)+rz^2)+eps^2) for
-//             both kinds of source, as in the reference (:164-171 and :198-213)
-template <bool FIXED>
-__global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkArgs a)
+//   evaluate  EXACT: R = x_i - x_src, f = G m / r^3 with sqrt(((rx^2+ry^2)+rz^2)+eps^2), r*r*r and a division, three
+//             multiply-subtract pairs, as in the reference (:164-171 and :198-213); else eval_fast()
+template <bool FIXED, bool EXACT>
+__global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkArgs a, long long slots)
 {
-    __shared__ double s_cell2[MAX_LEVEL + 2];
-    if (threadIdx.x < MAX_LEVEL + 2) s_cell2[threadIdx.x] = a.cell2[threadIdx.x];
+    __shared__ double s_cell2[MAX_LEVEL + 3];
+    if (threadIdx.x < MAX_LEVEL + 1) s_cell2[threadIdx.x] = a.meta->cell2[threadIdx.x];
     __syncthreads();
-    int q = a.p_lo + blockIdx.x * WALK_BLOCK + threadIdx.x;
-    if (a.world > 1) {
-        // interleaved chunks: walk cost varies smoothly along the Morton curve (dense centre vs halo), so every rank
-        // gets a sample of all regions instead of one contiguous stretch
-        const int t = blockIdx.x * WALK_BLOCK + threadIdx.x;
-        q = ((t / a.chunk) * a.world + a.rank) * a.chunk + t % a.chunk;
-    }
-    if (q >= a.p_hi) return;
-    const int p = a.tord ? a.tord[q] : q;
+    if (a.meta->overflow) return;
+    const long long t = (long long)blockIdx.x * WALK_BLOCK + threadIdx.x;
+    if (t >= slots) return;
+    const long long q = slot_to_position(a, t);
+    if (q >= a.n) return;
+    const int p = a.tord ? a.tord[q] : (int)q;
     const int idx = a.perm[p];
     const double4 me = a.psorted[p];
     const double xi = me.x, yi = me.y, zi = me.z;
@@ -112,14 +251,9 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
     double ax = 0.0, ay = 0.0, az = 0.0;
 
     int node = __ldg(&a.topo[0].fc);   // the root is always expanded
-#if WALK_VARIANT == 0
     NodeRec rec = load_rec(a.geo, a.topo, node);
-#endif
     int leaf_pos = 0, leaf_rem = 0, leaf_next = -1;
     while (node >= 0) {
-#if WALK_VARIANT == 1
-        const NodeRec rec = load_rec(a.geo, a.topo, node);
-#endif
         bool have = false;              // this trip produced a source
         bool from_node = false;         // ... which is the current node (else: particle at sorted position src_pos)
         int src_pos = 0;
@@ -130,7 +264,7 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
             const long long kq = rec.kq;
             const int fc = (int)rec.fc_next, next = (int)(rec.fc_next >> 32), first = (int)rec.first_lc;
             const int lc = (int)(rec.first_lc >> 32);
-            const int level = lc >> WALK_COUNT_BITS, count = lc & ((1 << WALK_COUNT_BITS) - 1);
+            const int level = lc >> WALK_COUNT_BITS, count = lc & COUNT_MASK;
             const int shift = 3 * (MAX_LEVEL - level);
             const bool leaf = fc < 0;
             const bool inside = ((ki ^ kq) >> shift) == 0;
@@ -171,35 +305,36 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
                 msrc = __longlong_as_double(qw);
             }
         }
-#if WALK_VARIANT == 0
         if (new_node != node && new_node >= 0) rec = load_rec(a.geo, a.topo, new_node);
-#else
-        if (new_node != node && new_node >= 0) prefetch_l1(a.geo + new_node);
-#endif
         node = new_node;
         if (have) {
-            const double rx = __dsub_rn(xi, sx), ry = __dsub_rn(yi, sy), rz = __dsub_rn(zi, sz);
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-            const double s = __dadd_rn(d2, a.eps2);
-            const double gm = __dmul_rn(a.G, msrc);
-            double f;
-            if (gm == 0.0 && s > 1e-200 && s < 1e200) {
-                f = gm;     // 0 / r^3 with r^3 finite and positive: exactly the signed zero gm (dropped zero-mass leaves)
+            if (EXACT) {
+                const double rx = __dsub_rn(xi, sx), ry = __dsub_rn(yi, sy), rz = __dsub_rn(zi, sz);
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                const double s = __dadd_rn(d2, a.eps2);
+                const double gm = __dmul_rn(a.G, msrc);
+                double f;
+                if (gm == 0.0 && s > 1e-200 && s < 1e200) {
+                    f = gm;     // 0 / r^3 with r^3 finite and positive: exactly the signed zero gm (dropped zero-mass leaves)
+                } else {
+                    const double r = __dsqrt_rn(s);
+                    f = __ddiv_rn(gm, __dmul_rn(__dmul_rn(r, r), r));
+                }
+                ax = __dsub_rn(ax, __dmul_rn(f, rx));
+                ay = __dsub_rn(ay, __dmul_rn(f, ry));
+                az = __dsub_rn(az, __dmul_rn(f, rz));
             } else {
-                const double r = __dsqrt_rn(s);
-                f = __ddiv_rn(gm, __dmul_rn(__dmul_rn(r, r), r));
+                eval_fast(sx, sy, sz, msrc, xi, yi, zi, a.eps2, ax, ay, az);
             }
-            ax = __dsub_rn(ax, __dmul_rn(f, rx));
-            ay = __dsub_rn(ay, __dmul_rn(f, ry));
-            az = __dsub_rn(az, __dmul_rn(f, rz));
         }
     }
-    a.acc[3 * (size_t)idx + 0] = ax;
-    a.acc[3 * (size_t)idx + 1] = ay;
-    a.acc[3 * (size_t)idx + 2] = az;
+    if (!EXACT) { ax *= a.G; ay *= a.G; az *= a.G; }
+    double *dst = a.out_slots ? a.out_slots + 3 * (size_t)t : a.acc + 3 * (size_t)idx;
+    dst[0] = ax;
+    dst[1] = ay;
+    dst[2] = az;
 }
 
-int bh_pack_walk_nodes(grav_b200_ctx *c);
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift);
 
 // walk key of every sorted position (reference mode: the sorted key array indexed by the ORIGINAL particle id)
@@ -210,36 +345,49 @@ __global__ void __launch_bounds__(256) walk_keys_kernel(const long long *__restr
     if (p < n) { ki[p] = K[perm[p]]; pos[p] = p; }
 }
 
+// multi-GPU: the gathered per-rank slot-ordered results -> acc[particle id]
+__global__ void __launch_bounds__(256) walk_scatter_kernel(const double *__restrict__ gathered, const int *__restrict__ perm, int n,
+                                                          int chunk, int world, long long slots_per_rank, double *__restrict__ acc)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;     // sorted position
+    if (q >= n) return;
+    const int ch = q / chunk;
+    const int r = ch % world;
+    const long long t = (long long)(ch / world) * chunk + q % chunk;
+    const double *src = gathered + 3 * ((size_t)r * slots_per_rank + (size_t)t);
+    const int idx = perm[q];
+    acc[3 * (size_t)idx + 0] = src[0];
+    acc[3 * (size_t)idx + 1] = src[1];
+    acc[3 * (size_t)idx + 2] = src[2];
+}
+
 int bh_walk(grav_b200_ctx *c, double eps, double theta)
 {
     DevTree &t = c->tree;
-    GB_TRY(bh_pack_walk_nodes(c));
+    const int n = c->n;
     WalkArgs a{};
-    a.geo = t.node_walk.as<WalkGeo>();
-    a.topo = reinterpret_cast<const WalkTopo *>(a.geo + t.num_nodes);
+    a.geo = t.geo();
+    a.topo = t.topo();
+    a.meta = t.meta.as<TreeMeta>();
     a.K = t.keys.as<long long>();
     a.perm = t.perm.as<int>();
     a.psorted = t.posm_sorted.as<double4>();
-    // ranks share the walk by sorted position, not by particle id: interleaved chunks of WALK_CHUNK positions
-    // (contiguous equal-count slices left the rank holding a Plummer sphere's centre 12 % behind at N = 2^24)
-    a.p_lo = 0;
-    a.p_hi = c->n;
+    a.n = n;
     a.chunk = WALK_CHUNK; a.rank = c->rank; a.world = c->world;
     a.G = c->G;
     a.eps2 = eps * eps;
     a.theta2 = theta * theta;
-    const double box_length = t.box_width * 2.0;          // src/acceleration_barnes_hut.c:100
-    for (int level = 0; level <= MAX_LEVEL; level++) {
-        const double bl = box_length / (double)(2 << level);   // :157
-        a.cell2[level] = bl * bl;                              // :162 (left-hand side)
-    }
     a.acc = c->acc.as<double>();
-    // Reference mode only: the walk length of a target depends on the top bits of its (unrelated) walk key, so
-    // Morton neighbours diverge.  Grouping targets by the key's level-1 octant (stable, Morton order inside a group)
-    // raises the item-count lane efficiency from 0.73 to 0.87 on a Plummer sphere (oracle statistics).
+    const bool fixed = c->bh_mode == GRAV_B200_BH_FIXED;
+    const bool exact = c->bh_exact != 0;
+    static const char *kernel_env = getenv("GRAV_B200_WALK_KERNEL");
+    const bool per_lane = exact || (kernel_env && strcmp(kernel_env, "lane") == 0);
+
+    // Per-lane kernel, reference mode only: the walk length of a target depends on the top bits of its (unrelated) walk
+    // key, so Morton neighbours diverge.  Grouping targets by the key's level-1 octant (stable, Morton order inside a
+    // group) raises the item-count lane efficiency from 0.73 to 0.87 on a Plummer sphere (Plummer -7 %, uniform +15 %).
     static const int group_bits = getenv("GRAV_B200_WALK_GROUP_BITS") ? atoi(getenv("GRAV_B200_WALK_GROUP_BITS")) : 0;
-    if (group_bits > 0 && c->bh_mode != GRAV_B200_BH_FIXED) {
-        const int n = c->n;
+    if (per_lane && group_bits > 0 && !fixed && c->world == 1) {
         GB_TRY(t.ki.reserve(sizeof(long long) * 2 * (size_t)n));
         GB_TRY(t.tord.reserve(sizeof(int) * 2 * (size_t)n));
         long long *ki = t.ki.as<long long>();
@@ -250,21 +398,50 @@ int bh_walk(grav_b200_ctx *c, double eps, double theta)
         GB_TRY(radix_pass(c, ki, pos + n, ki + n, pos, n, 63 - group_bits));   // digit = top group_bits bits (<= 8)
         a.tord = pos;
     }
-    if (c->world > 1) GB_CUDA(cudaMemsetAsync(a.acc, 0, sizeof(double) * 3 * (size_t)c->n, c->stream));
-    int npos = a.p_hi - a.p_lo;
-    if (c->world > 1) {   // slots of this rank: its share of the WALK_CHUNK-sized chunks (the last one may be partial)
-        const int chunks = (c->n + WALK_CHUNK - 1) / WALK_CHUNK;
-        const int mine = chunks > c->rank ? (chunks - c->rank + c->world - 1) / c->world : 0;
-        npos = mine * WALK_CHUNK;
+
+    // ranks share the walk by sorted position, not by particle id: interleaved chunks of WALK_CHUNK positions
+    // (contiguous equal-count slices left the rank holding a Plummer sphere's centre 12 % behind at N = 2^24)
+    long long slots = n, slots_per_rank = 0;
+    double *gathered = nullptr;
+    if (c->world > 1) {
+        const long long chunks = ((long long)n + WALK_CHUNK - 1) / WALK_CHUNK;
+        slots = chunks > c->rank ? ((chunks - c->rank + c->world - 1) / c->world) * WALK_CHUNK : 0;
+        slots_per_rank = ((chunks + c->world - 1) / c->world) * WALK_CHUNK;
+        GB_TRY(t.walk_out.reserve(sizeof(double) * 3 * (size_t)slots_per_rank * c->world));
+        gathered = t.walk_out.as<double>();
+        a.out_slots = gathered + 3 * (size_t)slots_per_rank * c->rank;
     }
-    if (npos > 0) {
-        const int blocks = (npos + WALK_BLOCK - 1) / WALK_BLOCK;
-        if (c->bh_mode == GRAV_B200_BH_FIXED) walk_kernel<true><<<blocks, WALK_BLOCK, 0, c->stream>>>(a);
-        else walk_kernel<false><<<blocks, WALK_BLOCK, 0, c->stream>>>(a);
+    if (slots > 0) {
+        if (per_lane) {
+            const unsigned blocks = (unsigned)((slots + WALK_BLOCK - 1) / WALK_BLOCK);
+            if (exact) {
+                if (fixed) walk_kernel<true, true><<<blocks, WALK_BLOCK, 0, c->stream>>>(a, slots);
+                else walk_kernel<false, true><<<blocks, WALK_BLOCK, 0, c->stream>>>(a, slots);
+            } else {
+                if (fixed) walk_kernel<true, false><<<blocks, WALK_BLOCK, 0, c->stream>>>(a, slots);
+                else walk_kernel<false, false><<<blocks, WALK_BLOCK, 0, c->stream>>>(a, slots);
+            }
+        } else {
+            // consecutive targets of a warp revisit almost the same nodes (L1 hits); fewer targets per warp when the
+            // system is too small to give every SM four waves of warps
+            int tpw = 8;
+            while (tpw > 1 && (slots + tpw - 1) / tpw < (long long)c->sm_count * 32 * 4) tpw >>= 1;
+            const long long warps = (slots + tpw - 1) / tpw;
+            const unsigned blocks = (unsigned)((warps + CW_WARPS - 1) / CW_WARPS);
+            if (fixed) walk_coop_kernel<true><<<blocks, CW_WARPS * 32, 0, c->stream>>>(a, tpw, slots);
+            else walk_coop_kernel<false><<<blocks, CW_WARPS * 32, 0, c->stream>>>(a, tpw, slots);
+        }
         GB_LAUNCH_CHECK();
         count_launch();
     }
-    if (c->world > 1) GB_TRY(comm_allreduce_sum(c, a.acc, 3 * c->n));   // disjoint targets + zeros: exact
+    if (c->world > 1) {
+        // every rank receives every rank's slot-ordered results (24 N bytes in all, half of what the round-1 all-reduce of
+        // zero-padded full arrays moved, and no memset), then scatters them to particle order
+        GB_TRY(comm_allgather_equal(c, gathered, 3 * (size_t)slots_per_rank));
+        walk_scatter_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(gathered, a.perm, n, WALK_CHUNK, c->world, slots_per_rank, a.acc);
+        GB_LAUNCH_CHECK();
+        count_launch();
+    }
     return GRAV_B200_OK;
 }
 

@@ -67,6 +67,13 @@ int comm_allgather_aos3(grav_b200_ctx *c, double *d_buf)
     return allgather_var(c, (char *)d_buf, 3 * sizeof(double));
 }
 
+int comm_allgather_equal(grav_b200_ctx *c, double *d_base, size_t count_per_rank)
+{
+    if (c->world == 1 || count_per_rank == 0) return GRAV_B200_OK;
+    GB_NCCL(ncclAllGather(d_base + (size_t)c->rank * count_per_rank, d_base, count_per_rank, ncclDouble, (ncclComm_t)c->comm, c->stream));
+    return GRAV_B200_OK;
+}
+
 int comm_allreduce_sum(grav_b200_ctx *c, double *d_val, int count)
 {
     if (c->world == 1) return GRAV_B200_OK;

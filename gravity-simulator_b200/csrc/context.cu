@@ -119,6 +119,7 @@ int unpack_positions(grav_b200_ctx *c, double *d_x)
 static std::mutex g_mu;
 static grav_b200_ctx *g_default = nullptr;
 static int g_bh_mode = -1;
+static int g_bh_exact = -1;
 
 static int default_ctx(grav_b200_ctx **out)
 {
@@ -132,6 +133,7 @@ static int default_ctx(grav_b200_ctx **out)
     // (a non-main Python thread, grav_sim/simulator.py:61-103): bind the device there
     GB_CUDA(cudaSetDevice(g_default->device));
     g_default->bh_mode = grav_b200_get_bh_mode();
+    g_default->bh_exact = grav_b200_get_bh_exact();
     *out = g_default;
     return GRAV_B200_OK;
 }
@@ -185,6 +187,21 @@ int grav_b200_get_bh_mode(void)
     return g_bh_mode;
 }
 
+int grav_b200_set_bh_exact(int on)
+{
+    g_bh_exact = on ? 1 : 0;
+    return GRAV_B200_OK;
+}
+
+int grav_b200_get_bh_exact(void)
+{
+    if (g_bh_exact < 0) {
+        const char *e = getenv("GRAV_B200_BH_EXACT");
+        g_bh_exact = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return g_bh_exact;
+}
+
 int grav_b200_ctx_create(grav_b200_ctx **out, int device, int rank, int world_size, const void *uid)
 {
     if (!out) { set_error("NULL out pointer"); return GRAV_B200_EINVAL; }
@@ -212,10 +229,13 @@ int grav_b200_ctx_create(grav_b200_ctx **out, int device, int rank, int world_si
     c->world = world_size;
     c->sm_count = prop.multiProcessorCount;
     c->bh_mode = grav_b200_get_bh_mode();
+    c->bh_exact = grav_b200_get_bh_exact();
+    if (const char *sl = getenv("GRAV_B200_TREE_SLACK")) { const int v = atoi(sl); if (v >= 1 && v <= 16) c->tree.slack = v; }
     cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) { delete c; return cuda_fail(se, "cudaStreamCreate", __FILE__, __LINE__); }
-    for (int i = 0; i < 2 * ST_COUNT; i++) cudaEventCreate(&c->ev[i]);
-    for (int i = 0; i < 8; i++) cudaEventCreate(&c->user_ev[i]);
+    for (int i = 0; i < 2 * ST_COUNT && se == cudaSuccess; i++) se = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 8 && se == cudaSuccess; i++) se = cudaEventCreate(&c->user_ev[i]);
+    if (se != cudaSuccess) { grav_b200_ctx_destroy(c); return cuda_fail(se, "cudaEventCreate", __FILE__, __LINE__); }
     if (world_size > 1) {
         int rc = comm_init(c, uid);
         if (rc != GRAV_B200_OK) { grav_b200_ctx_destroy(c); return rc; }
@@ -236,9 +256,11 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     for (DevBuf *b : bufs) b->release();
     DevTree &t = c->tree;
     DevBuf *tb[] = {&t.keys_unsorted, &t.keys, &t.perm, &t.keys_tmp, &t.perm_tmp, &t.hist, &t.bbox, &t.exp_rec,
-                    &t.wsum, &t.wscan, &t.scan_tmp, &t.fc, &t.node_np, &t.node_nch, &t.node_first, &t.node_fc, &t.node_mass,
-                    &t.node_cx, &t.node_cy, &t.node_cz, &t.node_mtd, &t.node_walk, &t.posm_sorted, &t.ki, &t.tord, &t.counters};
+                    &t.wsum, &t.wscan, &t.scan_tmp, &t.meta, &t.node_mtd, &t.node_walk, &t.posm_sorted, &t.ki, &t.tord,
+                    &t.walk_out, &t.xport};
     for (DevBuf *b : tb) b->release();
+    if (t.h_meta) cudaFreeHost(t.h_meta);
+    t.h_meta = nullptr;
     for (int i = 0; i < 2 * ST_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; i++) if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
     if (c->small_pinned) cudaFreeHost(c->small_pinned);
@@ -253,7 +275,8 @@ void grav_b200_ctx_owned_range(const grav_b200_ctx *c, int *lo, int *hi)
     if (hi) *hi = c ? c->hi : 0;
 }
 
-int grav_b200_ctx_set_system(grav_b200_ctx *c, int n, const double *x, const double *v, const double *m, double G)
+// need_vel = false: the caller never reads velocities (host-pointer one-shots), so a NULL v costs nothing
+static int set_system_impl(grav_b200_ctx *c, int n, const double *x, const double *v, const double *m, double G, bool need_vel)
 {
     if (!c) { set_error("NULL context"); return GRAV_B200_EINVAL; }
     if (!x || !m) { set_error("NULL array pointer"); return GRAV_B200_EINVAL; }
@@ -281,9 +304,14 @@ int grav_b200_ctx_set_system(grav_b200_ctx *c, int n, const double *x, const dou
     GB_CUDA(cudaMemcpyAsync(c->stage_b.p, m, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     GB_TRY(pack_posm(c, c->stage_a.as<double>(), c->stage_b.as<double>()));
     if (v) GB_CUDA(cudaMemcpyAsync(c->vel.p, v, b3, cudaMemcpyHostToDevice, c->stream));
-    else GB_CUDA(cudaMemsetAsync(c->vel.p, 0, b3, c->stream));
+    else if (need_vel) GB_CUDA(cudaMemsetAsync(c->vel.p, 0, b3, c->stream));
     c->posm_gathered = true;
     return GRAV_B200_OK;
+}
+
+int grav_b200_ctx_set_system(grav_b200_ctx *c, int n, const double *x, const double *v, const double *m, double G)
+{
+    return set_system_impl(c, n, x, v, m, G, true);
 }
 
 int grav_b200_ctx_set_positions(grav_b200_ctx *c, const double *x)
@@ -347,7 +375,7 @@ static int download_aos3(grav_b200_ctx *c, double *d_src, double *h_dst, bool sh
     if (sharded && c->world > 1) GB_TRY(comm_allgather_aos3(c, d_src));
     GB_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * 3 * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
     GB_CUDA(cudaStreamSynchronize(c->stream));
-    return GRAV_B200_OK;
+    return bh_check(c);
 }
 
 int grav_b200_ctx_get_positions(grav_b200_ctx *c, double *x)
@@ -377,7 +405,7 @@ int grav_b200_ctx_synchronize(grav_b200_ctx *c)
     if (!c) { set_error("NULL context"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     GB_CUDA(cudaStreamSynchronize(c->stream));
-    return GRAV_B200_OK;
+    return bh_check(c);
 }
 
 int grav_b200_ctx_last_timing_ms(grav_b200_ctx *c, int stage, float *ms)
@@ -445,9 +473,15 @@ static int one_shot(double *a, int n, const double *x, const double *m, double G
     std::lock_guard<std::mutex> lk(g_mu);
     grav_b200_ctx *c;
     GB_TRY(default_ctx(&c));
-    GB_TRY(grav_b200_ctx_set_system(c, n, x, nullptr, m, G));
-    GB_TRY(grav_b200_ctx_acceleration(c, method, eps, theta, leaf));
-    return grav_b200_ctx_get_accelerations(c, a);
+    GB_TRY(set_system_impl(c, n, x, nullptr, m, G, false));
+    for (;;) {
+        GB_TRY(grav_b200_ctx_acceleration(c, method, eps, theta, leaf));
+        const int rc = grav_b200_ctx_get_accelerations(c, a);
+        // Barnes-Hut builds are queued without waiting for their sizes; a tree that outgrew its buffers is reported by
+        // the download's synchronisation: rebuild with twice the room (the system is still resident)
+        if (rc != GRAV_B200_ETREE || c->tree.slack >= 16) return rc;
+        c->tree.slack *= 2;
+    }
 }
 
 int grav_b200_acceleration_pairwise(double *a, int n, const double *x, const double *m, double G, double eps)
@@ -489,7 +523,7 @@ static int whfast_one_shot(double *a, int n, const double *x, const double *m, d
     std::lock_guard<std::mutex> lk(g_mu);
     grav_b200_ctx *c;
     GB_TRY(default_ctx(&c));
-    GB_TRY(grav_b200_ctx_set_system(c, n, x, nullptr, m, G));
+    GB_TRY(set_system_impl(c, n, x, nullptr, m, G, false));
     const size_t b3 = sizeof(double) * 3 * (size_t)n;
     GB_TRY(c->stage_c.reserve(b3));
     GB_TRY(c->stage_d.reserve(sizeof(double) * (size_t)n));

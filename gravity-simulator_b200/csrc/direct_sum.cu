@@ -24,29 +24,6 @@
 
 namespace gb {
 
-__device__ __forceinline__ double rsqrt_seed(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    return y;
-}
-
-// m_j * r2^(-3/2), 7 FP64-pipe instructions + 1 MUFU.
-__device__ __forceinline__ double inv_r3_times_m(double r2, double mj)
-{
-    const double y = rsqrt_seed(r2);
-    const double t = y * y;                 // exact: y has <= 24 significant bits... (<=53 anyway)
-    const double e = fma(-r2, t, 1.0);      // 1 - r2*y^2, |e| <~ 2^-20
-    const double my = mj * y;
-    const double y3m = my * t;              // m * y^3
-    const double p = fma(1.875, e, 1.5);    // 3/2 + 15/8 e
-    const double q = e * p;
-    // m*y^3*(1 + q).  Written so the DFMA has only two distinct register sources: on sm_100 a
-    // DFMA with three distinct register operands occupies the FP64 pipe for 3 cycles instead of 2
-    // (measured, scratch/fp64_micro.cu; DESIGN.md "FP64 pipe").
-    return fma(q, y3m, y3m);
-}
-
 struct DSArgs {
     const double4 *src;       // sources, zero padded to a multiple of DS_TJ
     const int *src_id;        // MASSLESS: particle id of each source; PAIRWISE: nullptr (id == j)

@@ -152,6 +152,22 @@ static int run_force(grav_b200_ctx *c)
     return grav_b200_ctx_acceleration(c, c->lf_method, c->lf_eps, c->lf_theta, c->lf_leaf);
 }
 
+// First force evaluation of a resident run.  Later Barnes-Hut builds are queued without waiting for their sizes, so this
+// one waits, rebuilds with more room if the tree did not fit, and leaves 2x headroom over what this tree needed.
+static int first_force_checked(grav_b200_ctx *c)
+{
+    for (;;) {
+        GB_TRY(run_force(c));
+        if (c->lf_method != GRAV_B200_METHOD_BARNES_HUT) return GRAV_B200_OK;
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        const int rc = bh_check(c);
+        if (rc == GRAV_B200_ETREE && c->tree.slack < 16) { c->tree.slack *= 2; continue; }
+        if (rc != GRAV_B200_OK) return rc;
+        if (2LL * c->tree.h_meta->num_expanded > c->tree.ne_cap && c->tree.slack < 16) c->tree.slack *= 2;
+        return GRAV_B200_OK;
+    }
+}
+
 static int kick(grav_b200_ctx *c, double dt, int half)
 {
     const size_t lo = 3 * (size_t)c->lo, hi = 3 * (size_t)c->hi;
@@ -244,7 +260,7 @@ int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *c, int method, double eps, doubl
     GB_CUDA(cudaMemsetAsync(c->vcomp.p, 0, b3, c->stream));
     c->lf_method = method; c->lf_eps = eps; c->lf_theta = theta; c->lf_leaf = max_leaf;
     c->lf_ready = false;
-    GB_TRY(run_force(c));               // a(x0), src/integrator.c:963
+    GB_TRY(first_force_checked(c));     // a(x0), src/integrator.c:963
     GB_TRY(kick(c, dt, 1));             // v_{1/2}, :973-982
     c->lf_dt = dt;
     c->lf_ready = true;
@@ -305,6 +321,10 @@ int grav_b200_ctx_fixed_begin(grav_b200_ctx *c, int integrator, int method, doub
     c->lf_method = method; c->lf_eps = eps; c->lf_theta = theta; c->lf_leaf = max_leaf;
     c->lf_ready = false;
     c->fixed_integrator = integrator;
+    if (method == GRAV_B200_METHOD_BARNES_HUT) {   // size the tree buffers on a throw-away build (see first_force_checked)
+        GB_TRY(bh_build_checked(c, max_leaf == -1 ? 1 : max_leaf, nullptr, -1.0));
+        if (2LL * c->tree.h_meta->num_expanded > c->tree.ne_cap && c->tree.slack < 16) c->tree.slack *= 2;
+    }
     return GRAV_B200_OK;
 }
 
@@ -375,7 +395,7 @@ int grav_b200_ctx_energy(grav_b200_ctx *c, double *energy)
     GB_TRY(comm_allreduce_sum(c, part, 1));
     GB_CUDA(cudaMemcpyAsync(energy, part, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     GB_CUDA(cudaStreamSynchronize(c->stream));
-    return GRAV_B200_OK;
+    return bh_check(c);
 }
 
 }  // extern "C"

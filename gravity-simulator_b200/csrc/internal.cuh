@@ -36,6 +36,34 @@ constexpr int DS_BLOCK = 256;   // threads per CTA
 constexpr int DS_TJ    = 256;   // sources per shared-memory tile (one per thread on load)
 constexpr int SRC_PAD  = DS_TJ; // particle buffers are zero-padded to a multiple of this
 
+// ---- m * r^-3 for the direct sum and the fast Barnes-Hut evaluation -------------------------
+// The seed y0 = rsqrt.approx.ftz.f64(r2) only looks at the high word of r2 (|e| <~ 2^-20 with e = 1 - r2*y0^2);
+// r2^-3/2 = y0^3 (1-e)^-3/2 = y0^3 (1 + e(3/2 + 15/8 e) + 35/16 e^3 + ...), and the dropped term is < 2^-58.
+#ifdef __CUDACC__
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// m_j * r2^(-3/2), 7 FP64-pipe instructions + 1 MUFU.
+__device__ __forceinline__ double inv_r3_times_m(double r2, double mj)
+{
+    const double y = rsqrt_seed(r2);
+    const double t = y * y;                 // exact: y has <= 24 significant bits... (<=53 anyway)
+    const double e = fma(-r2, t, 1.0);      // 1 - r2*y^2, |e| <~ 2^-20
+    const double my = mj * y;
+    const double y3m = my * t;              // m * y^3
+    const double p = fma(1.875, e, 1.5);    // 3/2 + 15/8 e
+    const double q = e * p;
+    // m*y^3*(1 + q).  Written so the DFMA has only two distinct register sources: on sm_100 a
+    // DFMA with three distinct register operands occupies the FP64 pipe for 3 cycles instead of 2
+    // (measured, scratch/fp64_micro.cu; DESIGN.md "FP64 pipe").
+    return fma(q, y3m, y3m);
+}
+#endif
+
 // A growable device buffer (never shrinks; contents undefined after a grow).
 struct DevBuf {
     void *p = nullptr;
@@ -48,13 +76,12 @@ struct DevBuf {
 // Timing stages (grav_b200_ctx_last_timing_ms)
 enum { ST_TOTAL = 0, ST_GATHER = 1, ST_FORCE = 2, ST_MORTON = 3, ST_SORT = 4, ST_BUILD = 5, ST_COUNT = 6 };
 
-// What the tree walk reads per node: one 64-byte record.  The first 48 bytes are needed at every visit,
-// the mass only when the node is accepted.
+// What the tree walk reads per node: two 32-byte records (geometry, topology), stored as two planes
+// (geo[m_cap] then topo[m_cap] in one buffer) rather than one 64-byte record: the walk is bound by L1 wavefronts =
+// distinct 128-byte lines per load instruction, and lanes that are a few siblings apart then share lines
+// (4 records per line instead of 2).
 // `next` is the "rope": the node that follows in depth-first order when this node's subtree is skipped
-// (next sibling, else the parent's rope; -1 ends the walk), which makes the walk stackless.
-// Stored as two planes of 32-byte records (geo[M] then topo[M] in one buffer) rather than one 64-byte record: the
-// walk is bound by L1 wavefronts = distinct 128-byte lines per load instruction, and lanes that are a few siblings
-// apart then share lines (4 records per line instead of 2).
+// (next sibling, else the parent's rope; -1 ends the walk), which makes the per-lane walk stackless.
 struct WalkGeo {
     double cx, cy, cz;
     long long kq;      // key the inclusion test compares against (mode dependent)
@@ -65,33 +92,50 @@ struct WalkTopo {
     int first;         // sorted position of the node's first particle
     int level_count;   // level << 26 | particles in the node (N <= 2^24 < 2^26)
     double mass;
-    long long pad;
+    int nch;           // number of children (0 for a leaf)
+    int pad;
 };
 constexpr int WALK_COUNT_BITS = 26;
 static_assert(sizeof(WalkGeo) == 32 && sizeof(WalkTopo) == 32, "walk record layout");
 
+// Device-side bookkeeping of one tree build.  Everything the later stages need to know about the sizes the earlier
+// stages produced lives HERE, on the device, so the host never waits for a count (no cudaStreamSynchronize between the
+// first and the last kernel of a force evaluation).  A copy lands in pinned host memory at the end of the build and is
+// looked at by the next call that synchronises anyway (download, energy, ctx_synchronize).
+struct TreeMeta {
+    int lvl_cnt[24];    // expanded records per level
+    int lvl_off[24];    // first record of each level
+    int num_expanded;   // records in total
+    int num_nodes;      // M = 1 + children of all expanded nodes
+    int levels;         // levels that hold expanded nodes
+    int overflow;       // bit 0: more expanded nodes than exp_rec holds, bit 1: more nodes than the node planes hold
+    double box_width;
+    double cell2[24];   // (box_length / (2 << level))^2 per child level, src/acceleration_barnes_hut.c:157,162
+};
+constexpr int TREE_OVERFLOW_EXPANDED = 1, TREE_OVERFLOW_NODES = 2;
+
 // Device-side linear octree (layout in DESIGN.md "BH data layout")
 struct DevTree {
     int n = 0;
-    int num_nodes = 0;           // valid after build (host copy)
-    int num_expanded = 0;
-    int max_level = 0;           // number of levels that hold expanded nodes
-    int level_off[24] = {};      // expanded-node records of level l are [level_off[l], level_off[l+1])
-    double box_width = 0.0;
+    int ne_cap = 0, m_cap = 0;   // capacities of exp_rec and of the node planes in the current build
+    int slack = 1;               // capacity multiplier (doubled after an overflow)
+    bool built = false;          // a build has been queued since the last successful check
     DevBuf keys_unsorted, keys, perm;       // int64[n], int64[n], int[n]
     DevBuf keys_tmp, perm_tmp, hist;        // radix sort ping-pong + histograms
     DevBuf bbox;                            // double[8]: min xyz, max xyz (ordered-int encoded), then center xyz + width as double[4]
-    DevBuf exp_rec;                         // expanded-node records in BFS order
+    DevBuf exp_rec;                         // expanded-node records, level by level
     DevBuf wsum, wscan;                     // int[n+1] children-per-start-position and its exclusive scan
     DevBuf scan_tmp;
-    DevBuf fc;                              // int[num_expanded] first-child id per expanded record
-    DevBuf node_np, node_nch, node_first, node_fc;      // int[num_nodes]
-    DevBuf node_mass, node_cx, node_cy, node_cz;        // double[num_nodes]
-    DevBuf node_mtd;                        // double[3*num_nodes] mass-weighted position sums
-    DevBuf node_walk;                       // packed 64-byte walk records
+    DevBuf meta;                            // TreeMeta
+    TreeMeta *h_meta = nullptr;             // pinned host mirror (valid after the stream reached the end of the build)
+    DevBuf node_walk;                       // geo[m_cap] then topo[m_cap]
+    DevBuf node_mtd;                        // double[3*m_cap] mass-weighted position sums
     DevBuf posm_sorted;                     // double4[n]: posm in sorted (Morton) order, for the walk's leaf sums
-    DevBuf ki, tord;                        // walk keys and target order (optional walk-key grouping)
-    DevBuf counters;                        // misc device ints
+    DevBuf ki, tord;                        // walk keys and target order (optional walk-key grouping of the per-lane walk)
+    DevBuf walk_out;                        // multi-GPU: per-rank walk results in slot order + the gathered copy
+    DevBuf xport;                           // construct_octree(): the LinearOctree arrays, derived from the planes on demand
+    WalkGeo *geo() const { return node_walk.as<WalkGeo>(); }
+    WalkTopo *topo() const { return reinterpret_cast<WalkTopo *>(node_walk.as<WalkGeo>() + m_cap); }
 };
 
 }  // namespace gb
@@ -130,6 +174,7 @@ struct grav_b200_ctx {
     void *wh = nullptr;   // gb::WhfastState (whfast_resident.cu)
 
     int bh_mode = 0;
+    int bh_exact = 0;             // 1: bit-identical per-lane walk (GRAV_B200_BH_EXACT), 0: warp-cooperative walk, <= 1e-12
     cudaEvent_t user_ev[8] = {};
     gb::DevBuf l2_flush;
     double *small_pinned = nullptr;   // mapped pinned host staging of the small-N one-shot path (in: 4n doubles, out: 3n)
@@ -151,6 +196,8 @@ int whfast_accel(grav_b200_ctx *c, const double *d_jacobi_x, const double *d_eta
 // bh_*.cu
 int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double box_width);
 int bh_walk(grav_b200_ctx *c, double eps, double theta);
+int bh_build_checked(grav_b200_ctx *c, int max_leaf, const double *box_center, double box_width);   // build + sync + retry
+int bh_check(grav_b200_ctx *c);   // after a host sync: did the last queued build fit its buffers?  (GRAV_B200_ETREE if not)
 // whfast_resident.cu
 void whfast_state_free(grav_b200_ctx *c);
 // comm.cu
@@ -159,6 +206,7 @@ void comm_destroy(grav_b200_ctx *c);
 int comm_allgather_posm(grav_b200_ctx *c);
 int comm_allgather_aos3(grav_b200_ctx *c, double *d_buf);   // gathers owned [3*lo,3*hi) slices in place
 int comm_allreduce_sum(grav_b200_ctx *c, double *d_val, int count);
+int comm_allgather_equal(grav_b200_ctx *c, double *d_base, size_t count_per_rank);   // in place: rank r's part at d_base + r * count
 // integrate.cu
 int leapfrog_kick(grav_b200_ctx *c, double dt_half_or_full);
 int leapfrog_drift(grav_b200_ctx *c, double dt);

@@ -37,6 +37,9 @@ extern "C" {
 #define GRAV_B200_ECUDA     3   /* any other CUDA runtime failure (maps to GRAV_FAILURE)         */
 #define GRAV_B200_ENODEV    4   /* no usable device / driver (maps to GRAV_FAILURE)              */
 #define GRAV_B200_ENCCL     5   /* NCCL failure (maps to GRAV_FAILURE)                           */
+#define GRAV_B200_ETREE     6   /* the octree outgrew its device buffers (pathologically deep chains).  Builds are queued
+                                 * without host synchronisation, so this surfaces at the next synchronising call; the
+                                 * host-pointer entries retry with larger buffers by themselves (maps to GRAV_FAILURE)  */
 
 /* acceleration methods: same encoding as src/acceleration.h:16-18 */
 #define GRAV_B200_METHOD_PAIRWISE   1
@@ -114,6 +117,18 @@ int grav_b200_morton_keys(int n, const double *x, int64_t *keys_unsorted,
  * environment variable GRAV_B200_BH_MODE=reference|fixed (read once). */
 int grav_b200_set_bh_mode(int mode);
 int grav_b200_get_bh_mode(void);
+
+/* Barnes-Hut walk arithmetic.  Every accept / open / leaf decision is always taken with the reference's IEEE operations
+ * in the reference's order, so the set of sources per particle is the reference's in both settings.
+ *   0 (default)  warp-cooperative walk; accepted sources are evaluated with the direct sum's fused arithmetic and summed
+ *                in a different order: accelerations agree with src/acceleration_barnes_hut.c:78-248 to <= 1e-12 relative
+ *                (the north-star tolerance; observed ~1e-15).
+ *   1            per-lane walk in the reference's depth-first order with sqrt / div / separate multiplies: accelerations
+ *                BIT-IDENTICAL to the x86-64 reference build, about 2-3x slower.
+ * Also settable with the environment variable GRAV_B200_BH_EXACT=1 (read once).  Applies to the one-shot entries and to
+ * contexts created afterwards. */
+int grav_b200_set_bh_exact(int on);
+int grav_b200_get_bh_exact(void);
 
 /* ---- (2) device-resident context ---------------------------------------------------- */
 

@@ -76,6 +76,12 @@ class Oracle:
         L.oracle_barnes_hut.argtypes = [dp, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
         L.oracle_energy.argtypes = [C.c_int, dp, dp, dp, C.c_double]
         L.oracle_energy.restype = C.c_double
+        for f in (L.oracle_pairwise_targets, L.oracle_pairwise_targets_ld):
+            f.argtypes = [dp, C.c_int, ip, C.c_int, dp, dp, C.c_double, C.c_double]
+            f.restype = None
+        L.oracle_bh_walk_targets.argtypes = [dp, C.POINTER(C.c_longlong), C.POINTER(OracleTree), dp, dp, C.c_double,
+                                             C.c_double, C.c_double, C.c_int, C.c_int, ip]
+        L.oracle_bh_walk_targets.restype = None
         L.oracle_sort_by_distance.argtypes = [C.c_int, ip, dp, dp, dp, C.c_int]
         L.oracle_whfast_eta.argtypes = [dp, C.c_int, dp]
         L.oracle_whfast_eta.restype = None
@@ -172,6 +178,54 @@ class Oracle:
     def energy(self, x, v, m, G):
         x = _f64(x, (-1, 3)); v = _f64(v, (-1, 3)); m = _f64(m, (-1,))
         return float(self.L.oracle_energy(m.shape[0], _d(x), _d(v), _d(m), G))
+
+    def pairwise_targets(self, x, m, G, softening_length, targets, long_double=False):
+        """Rows `targets` of the pairwise direct sum: the reference's operation order per target (bit-identical to
+        acceleration(..., "pairwise")[targets]), or the same sums in long double (the rounding-noise yardstick)."""
+        x = _f64(x, (-1, 3)); m = _f64(m, (-1,))
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        a = np.empty((t.shape[0], 3))
+        fn = self.L.oracle_pairwise_targets_ld if long_double else self.L.oracle_pairwise_targets
+        fn(_d(a), t.shape[0], t.ctypes.data_as(ip), m.shape[0], _d(x), _d(m), G, softening_length)
+        return a
+
+    def tree(self, x, m, max_num_particles_per_leaf=1):
+        """A built tree kept alive for several sampled walks (free it with .close() or use as a context manager)."""
+        return OracleTreeHandle(self, x, m, max_num_particles_per_leaf)
+
+
+class OracleTreeHandle:
+    def __init__(self, oracle, x, m, leaf):
+        self.O = oracle
+        self.x = _f64(x, (-1, 3)); self.m = _f64(m, (-1,)); self.n = self.m.shape[0]
+        self.t = OracleTree()
+        assert oracle.L.oracle_build_tree(C.byref(self.t), self.n, _d(self.x), _d(self.m), leaf, None, -1.0) == 0
+
+    def to_dict(self):
+        t = self.t
+        return _tree_dict(t.keys, t.perm, t.num_particles, t.num_children, t.first_particle, t.first_child,
+                          t.mass, t.com_x, t.com_y, t.com_z, self.n, t.num_nodes, t.box_width)
+
+    def walk_targets(self, G, softening_length, opening_angle, positions, fixed=False, stats=False):
+        """Accelerations of the particles at the given SORTED positions (row k belongs to particle
+        sorted_indices[positions[k]]); stats=True also returns (visits, accepts, opened, leaf particles) per target."""
+        pos = np.ascontiguousarray(positions, dtype=np.int32)
+        a = np.empty((pos.shape[0], 3))
+        st = np.zeros((pos.shape[0], 4), dtype=np.int64) if stats else None
+        self.O.L.oracle_bh_walk_targets(_d(a), st.ctypes.data_as(C.POINTER(C.c_longlong)) if stats else None, C.byref(self.t),
+                                        _d(self.x), _d(self.m), G, softening_length, opening_angle, int(fixed), pos.shape[0],
+                                        pos.ctypes.data_as(ip))
+        return (a, st) if stats else a
+
+    def close(self):
+        if self.t.keys:
+            self.O.L.oracle_free_tree(C.byref(self.t))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 # ---- the unmodified reference ---------------------------------------------------------------------------

@@ -40,6 +40,58 @@ void oracle_pairwise(double *a, int n, const double *x, const double *m, double 
         for (int j = i + 1; j < n; j++) pair_kick(a, x, i, j, m[i], m[j], G, eps2);
 }
 
+/* One target of oracle_pairwise(): the operations the reference's i<j loop applies to a[i], in the order it applies
+ * them -- pairs (j,i) with j < i arrive first, as the "+= fx*mi" half of pair_kick(j, i) in outer iteration j, then the
+ * pairs (i,j) with j > i in outer iteration i (src/acceleration.c:198-231).  Bit-identical to oracle_pairwise()[i]
+ * (tests/test_oracle.py), which makes reference comparisons affordable at N = 2^20 (a few hundred targets). */
+void oracle_pairwise_targets(double *a, int nt, const int *targets, int n, const double *x, const double *m, double G,
+                             double eps)
+{
+    const double eps2 = eps * eps;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int t = 0; t < nt; t++) {
+        const int i = targets[t];
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int j = 0; j < i; j++) {
+            const double rx = x[3 * j] - x[3 * i], ry = x[3 * j + 1] - x[3 * i + 1], rz = x[3 * j + 2] - x[3 * i + 2];
+            const double r = sqrt(rx * rx + ry * ry + rz * rz + eps2);
+            const double f = G / (r * r * r);
+            const double fx = f * rx, fy = f * ry, fz = f * rz;
+            ax += fx * m[j]; ay += fy * m[j]; az += fz * m[j];
+        }
+        for (int j = i + 1; j < n; j++) {
+            const double rx = x[3 * i] - x[3 * j], ry = x[3 * i + 1] - x[3 * j + 1], rz = x[3 * i + 2] - x[3 * j + 2];
+            const double r = sqrt(rx * rx + ry * ry + rz * rz + eps2);
+            const double f = G / (r * r * r);
+            const double fx = f * rx, fy = f * ry, fz = f * rz;
+            ax -= fx * m[j]; ay -= fy * m[j]; az -= fz * m[j];
+        }
+        a[3 * t] = ax; a[3 * t + 1] = ay; a[3 * t + 2] = az;
+    }
+}
+
+/* The same sum in extended precision (x87 long double, 64-bit significand): the yardstick that tells the reference's own
+ * rounding noise (serial double sum of N terms) from a real disagreement when N = 2^20. */
+void oracle_pairwise_targets_ld(double *a, int nt, const int *targets, int n, const double *x, const double *m, double G,
+                                double eps)
+{
+    const long double eps2 = (long double)eps * eps;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int t = 0; t < nt; t++) {
+        const int i = targets[t];
+        long double ax = 0.0L, ay = 0.0L, az = 0.0L;
+        for (int j = 0; j < n; j++) {
+            if (j == i) continue;
+            const long double rx = (long double)x[3 * i] - x[3 * j], ry = (long double)x[3 * i + 1] - x[3 * j + 1],
+                              rz = (long double)x[3 * i + 2] - x[3 * j + 2];
+            const long double r = sqrtl(rx * rx + ry * ry + rz * rz + eps2);
+            const long double f = (long double)m[j] / (r * r * r);
+            ax -= f * rx; ay -= f * ry; az -= f * rz;
+        }
+        a[3 * t] = (double)(G * ax); a[3 * t + 1] = (double)(G * ay); a[3 * t + 2] = (double)(G * az);
+    }
+}
+
 static int split_by_mass(int n, const double *m, int **massive, int *n_massive, int **massless, int *n_massless)
 {
     int *hv = malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
@@ -441,6 +493,8 @@ typedef struct WalkCtx {
     int self;
     int64_t key;
     double xi[3], acc[3];
+    /* statistics of the current target (oracle_bh_walk_stats) */
+    long long visits, accepts, opened, leaf_particles;
 } WalkCtx;
 
 static void walk_children(WalkCtx *w, int node, int level)
@@ -455,6 +509,7 @@ static void walk_children(WalkCtx *w, int node, int level)
          * (src/acceleration_barnes_hut.c:120,145) */
         const int64_t kc = w->fixed ? t->keys[s] : t->keys[t->perm[s]];
         const int inside = (w->key >> sh) == (kc >> sh);
+        w->visits++;
         if (!inside && !(w->fixed && is_leaf)) {
             const double rx = w->xi[0] - t->com_x[c], ry = w->xi[1] - t->com_y[c], rz = w->xi[2] - t->com_z[c];
             const double cell = w->box_length / (2 << level);
@@ -463,6 +518,7 @@ static void walk_children(WalkCtx *w, int node, int level)
                 const double r = sqrt(d2 + w->eps2);
                 const double f = w->G * t->mass[c] / (r * r * r);
                 w->acc[0] -= f * rx; w->acc[1] -= f * ry; w->acc[2] -= f * rz;
+                w->accepts++;
                 continue;
             }
         }
@@ -470,16 +526,20 @@ static void walk_children(WalkCtx *w, int node, int level)
             for (int p = s; p < s + t->num_particles[c]; p++) {
                 const int j = t->perm[p];
                 if (j == w->self) continue;
+                w->leaf_particles++;
                 const double rx = w->xi[0] - w->x[3 * j], ry = w->xi[1] - w->x[3 * j + 1], rz = w->xi[2] - w->x[3 * j + 2];
                 const double r = sqrt(rx * rx + ry * ry + rz * rz + w->eps2);
                 const double f = w->G * w->m[j] / (r * r * r);
                 w->acc[0] -= f * rx; w->acc[1] -= f * ry; w->acc[2] -= f * rz;
             }
         } else {
+            w->opened++;
             walk_children(w, c, level + 1);
         }
     }
 }
+
+static void walk_one(WalkCtx *w, const OracleTree *t, const double *x, int p, int fixed_mode);
 
 void oracle_bh_walk(double *a, const OracleTree *t, const double *x, const double *m, double G, double eps,
                     double theta, int fixed_mode)
@@ -490,12 +550,41 @@ void oracle_bh_walk(double *a, const OracleTree *t, const double *x, const doubl
     w.fixed = fixed_mode;
     for (int p = 0; p < t->n; p++) {
         const int i = t->perm[p];
-        w.self = i;
-        w.key = fixed_mode ? t->keys[p] : t->keys[i];
-        w.xi[0] = x[3 * i]; w.xi[1] = x[3 * i + 1]; w.xi[2] = x[3 * i + 2];
-        w.acc[0] = w.acc[1] = w.acc[2] = 0.0;
-        walk_children(&w, 0, 1);
+        walk_one(&w, t, x, p, fixed_mode);
         a[3 * i] = w.acc[0]; a[3 * i + 1] = w.acc[1]; a[3 * i + 2] = w.acc[2];
+    }
+}
+
+static void walk_one(WalkCtx *w, const OracleTree *t, const double *x, int p, int fixed_mode)
+{
+    const int i = t->perm[p];
+    w->self = i;
+    w->key = fixed_mode ? t->keys[p] : t->keys[i];
+    w->xi[0] = x[3 * i]; w->xi[1] = x[3 * i + 1]; w->xi[2] = x[3 * i + 2];
+    w->acc[0] = w->acc[1] = w->acc[2] = 0.0;
+    w->visits = w->accepts = w->opened = w->leaf_particles = 0;
+    walk_children(w, 0, 1);
+}
+
+/* oracle_bh_walk() for a subset of targets given by SORTED POSITION; a[3*k..] is the acceleration of particle
+ * perm[positions[k]].  Same code path per target, so bit-identical to the full walk (tests/test_oracle.py); this is what
+ * makes a reference comparison at N = 2^24 affordable.  stats (may be NULL): 4 counters per target -- nodes visited,
+ * nodes accepted, nodes opened, leaf particles summed directly. */
+void oracle_bh_walk_targets(double *a, long long *stats, const OracleTree *t, const double *x, const double *m, double G,
+                            double eps, double theta, int fixed_mode, int nt, const int *positions)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int k = 0; k < nt; k++) {
+        WalkCtx w;
+        w.t = t; w.x = x; w.m = m; w.G = G; w.eps2 = eps * eps; w.theta2 = theta * theta;
+        w.box_length = t->box_width * 2.0;
+        w.fixed = fixed_mode;
+        walk_one(&w, t, x, positions[k], fixed_mode);
+        a[3 * k] = w.acc[0]; a[3 * k + 1] = w.acc[1]; a[3 * k + 2] = w.acc[2];
+        if (stats) {
+            stats[4 * k] = w.visits; stats[4 * k + 1] = w.accepts; stats[4 * k + 2] = w.opened;
+            stats[4 * k + 3] = w.leaf_particles;
+        }
     }
 }
 

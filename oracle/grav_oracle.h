@@ -20,6 +20,12 @@
 
 /* src/acceleration.c:177-234 */
 void oracle_pairwise(double *a, int n, const double *x, const double *m, double G, double eps);
+/* the entries targets[0..nt) of oracle_pairwise()'s result, each with the reference's operation order for that target
+ * (bit-identical to the full loop); _ld: the same sums in long double, as a yardstick for rounding noise */
+void oracle_pairwise_targets(double *a, int nt, const int *targets, int n, const double *x, const double *m, double G,
+                             double eps);
+void oracle_pairwise_targets_ld(double *a, int nt, const int *targets, int n, const double *x, const double *m, double G,
+                                double eps);
 /* src/acceleration.c:236-367 (with the m[rank] indexing of :357-359) */
 int oracle_massless(double *a, int n, const double *x, const double *m, double G, double eps);
 /* src/integrator_whfast.c:839-957 and :959-1264; aux[] defined as zero-initialised */
@@ -53,6 +59,10 @@ void oracle_free_tree(OracleTree *t);
 /* src/acceleration_barnes_hut.c:78-248.  fixed_mode 0 = bug-for-bug, 1 = corrected walk. */
 void oracle_bh_walk(double *a, const OracleTree *t, const double *x, const double *m, double G,
                     double eps, double theta, int fixed_mode);
+/* the walk for the targets at the given sorted positions only (a[3k..] belongs to particle perm[positions[k]]);
+ * stats: NULL or 4 counters per target (visits, accepts, opened, leaf particles) */
+void oracle_bh_walk_targets(double *a, long long *stats, const OracleTree *t, const double *x, const double *m, double G,
+                            double eps, double theta, int fixed_mode, int nt, const int *positions);
 /* src/acceleration_barnes_hut.c:33-76 */
 int oracle_barnes_hut(double *a, int n, const double *x, const double *m, double G, double eps,
                       double theta, int max_leaf, int fixed_mode);

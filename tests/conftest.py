@@ -24,6 +24,7 @@ def load_package():
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "cooperative_walk: run with the default Barnes-Hut walk in a module that otherwise uses the exact one")
 
 
 @pytest.fixture(scope="session")
@@ -70,3 +71,31 @@ def max_rel_err(a, ref):
     den = np.linalg.norm(ref, axis=1)
     den = np.where(den > 0, den, 1.0)
     return float(np.max(num / den))
+
+
+def assert_forces_close(a, ref, tol=1e-12, ctx=""):
+    """Parity gate for accelerations whose summation order differs from the reference: the same
+    NaN / inf rows as the reference, and max_i |a_i - ref_i|_2 / |ref_i|_2 <= tol on the finite ones."""
+    import numpy as np
+    fin = np.isfinite(ref).all(axis=1)
+    assert np.array_equal(np.isfinite(a).all(axis=1), fin), (ctx, "finite pattern differs")
+    if fin.any():
+        err = max_rel_err(a[fin], ref[fin])
+        assert err <= tol, (ctx, err)
+
+
+class bh_exact:
+    """with bh_exact(gb, 1): ...   -- Barnes-Hut walk arithmetic for the one-shot entries and contexts created inside
+    (include/grav_b200.h, grav_b200_set_bh_exact): 1 = bit-identical per-lane walk, 0 = warp-cooperative walk (default)."""
+
+    def __init__(self, gb, on):
+        self.abi, _ = gb.load()
+        self.on = int(on)
+
+    def __enter__(self):
+        self.prev = int(self.abi.grav_b200_get_bh_exact())
+        self.abi.grav_b200_set_bh_exact(self.on)
+        return self
+
+    def __exit__(self, *exc):
+        self.abi.grav_b200_set_bh_exact(self.prev)

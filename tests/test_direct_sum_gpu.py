@@ -89,6 +89,28 @@ def test_full_size_properties(gb, ics):
     assert max_rel_err(a3, a) <= 1e-15
 
 
+@pytest.mark.parametrize("eps", [0.01, 0.0])
+def test_bench_size_sampled_targets_vs_reference_order(gb, oracle, ics, eps):
+    """N = 2^20 -- the headline bench size, stream-K split + fix-up (eps > 0) and fast + special-tile kernels (eps = 0)
+    -- against the reference's own arithmetic for 512 sampled targets x all sources (oracle.pairwise_targets repeats, per
+    target, the operations of src/acceleration.c:198-231 in their order; pinned bit-equal to the compiled reference in
+    tests/test_oracle.py).  The 64 innermost particles of the sphere are in the sample: their forces cancel the most.
+    Also shown: the GPU is no further from a long-double evaluation than the reference itself is."""
+    n = 1 << 20
+    x, v, m, G = ics.plummer(n, 42)
+    r = np.linalg.norm(x, axis=1)
+    tg = np.concatenate([np.argsort(r)[:64], np.random.default_rng(1).choice(n, 448, replace=False)]).astype(np.int32)
+    a = gb.acceleration(x, m, G, "pairwise", eps)
+    ref = oracle.pairwise_targets(x, m, G, eps, tg)
+    assert max_rel_err(a[tg], ref) <= TOL
+    truth = oracle.pairwise_targets(x, m, G, eps, tg, long_double=True)
+    assert max_rel_err(a[tg], truth) <= max(max_rel_err(ref, truth), 1e-14)
+    # size-independent properties on the full vector
+    assert np.isfinite(a).all()
+    mom = (m[:, None] * a).sum(0)
+    assert np.abs(mom).max() <= 1e-11 * np.abs(m[:, None] * a).sum()
+
+
 def test_context_resident_matches_one_shot(gb, ics):
     x, v, m, G = ics.uniform_cube(5000, seed=8)
     with gb.Context() as c:

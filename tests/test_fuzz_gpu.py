@@ -1,9 +1,10 @@
 """GPU parity fuzz: seeded random systems with awkward geometry (planar, collinear, duplicates, huge dynamic range,
-zero masses, tiny N) through every method, against the CPU oracle.  Barnes-Hut outputs must be bit-identical."""
+zero masses, tiny N) through every method, against the CPU oracle.  Barnes-Hut trees must be bit-identical, and so must
+the accelerations of the exact walk; the default cooperative walk and the direct sums are held to 1e-12."""
 import numpy as np
 import pytest
 
-from conftest import max_rel_err
+from conftest import bh_exact, max_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -43,13 +44,18 @@ def test_fuzz_all_methods(gb, oracle, seed):
     assert t["num_nodes"] == to["num_nodes"] and (t["box_width"] == to["box_width"] or np.isnan(to["box_width"]))
     for k in ("keys", "sorted_indices", "num_particles", "num_children", "first_particle", "first_child", "mass", "com_x", "com_y", "com_z"):
         assert np.array_equal(t[k], to[k], equal_nan=True), (seed, k)
-    a = gb.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
+    with bh_exact(gb, 1):
+        a = gb.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
     ao = oracle.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
     assert np.array_equal(a, ao, equal_nan=True), (seed, "bh", max_rel_err(np.nan_to_num(a), np.nan_to_num(ao)))
-    # direct sums: 1e-12 on every particle where the reference is finite and non-zero; NaN/inf pattern identical
-    for method in ("pairwise", "massless"):
-        a = gb.acceleration(x, m, G, method, eps)
-        ao = oracle.acceleration(x, m, G, method, eps)
+    # cooperative Barnes-Hut walk and direct sums: 1e-12 on every particle where the reference is finite and non-zero;
+    # NaN/inf pattern identical
+    for method in ("barnes_hut", "pairwise", "massless"):
+        if method == "barnes_hut":
+            a = gb.acceleration(x, m, G, method, eps, theta, leaf)
+        else:
+            a = gb.acceleration(x, m, G, method, eps)
+            ao = oracle.acceleration(x, m, G, method, eps)
         fin = np.isfinite(ao).all(axis=1)
         assert np.array_equal(np.isfinite(a).all(axis=1), fin), (seed, method, "finite pattern")
         if fin.any():

@@ -132,3 +132,28 @@ def test_oracle_whfast_vs_reference_live(oracle, reference, ics, monkeypatch):
         assert np.array_equal(sr[q], so[q]), q
     for z in (0.0, 0.05, -0.09, 0.3, -7.5, 123.456, -1e4, 3e7):
         assert np.array_equal(reference.stumpff(z), oracle.stumpff(z)), z
+
+
+def test_sampled_target_functions_are_the_full_loops(oracle, reference, golden, ics):
+    """The sampled-target entries (used for reference comparisons at N = 2^20 / 2^24, where the full CPU loops take an
+    hour) give bit for bit the rows of the full restatement AND of the compiled reference."""
+    rng = np.random.default_rng(5)
+    for x, v, m, G in (ics.plummer(3000, 11), ics.clustered(2000, 12)):
+        for eps in (0.0, 0.01):
+            tg = rng.choice(m.shape[0], 200, replace=False)
+            full = reference.acceleration(x, m, G, "pairwise", eps)
+            got = oracle.pairwise_targets(x, m, G, eps, tg)
+            assert np.array_equal(got, full[tg], equal_nan=True)
+            ld = oracle.pairwise_targets(x, m, G, eps, tg, long_double=True)
+            ok = np.isfinite(full[tg]).all(axis=1)
+            assert max_rel_err(ld[ok], full[tg][ok]) < 1e-12
+        for theta, leaf, fixed in ((0.5, 1, False), (1.0, 3, False), (0.3, 1, True)):
+            with oracle.tree(x, m, leaf) as t:
+                pos = rng.choice(m.shape[0], 300, replace=False)
+                a, st = t.walk_targets(G, 0.01, theta, pos, fixed=fixed, stats=True)
+                perm = t.to_dict()["sorted_indices"]
+            full = oracle.acceleration(x, m, G, "barnes_hut", 0.01, theta, leaf, fixed=fixed)
+            assert np.array_equal(a, full[perm[pos]], equal_nan=True)
+            if not fixed:
+                assert np.array_equal(a, reference.acceleration(x, m, G, "barnes_hut", 0.01, theta, leaf)[perm[pos]], equal_nan=True)
+            assert (st[:, 0] == st[:, 1] + st[:, 2] + (st[:, 0] - st[:, 1] - st[:, 2])).all() and (st[:, 0] > 0).all()

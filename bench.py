@@ -13,7 +13,11 @@ value  = ordered pair interactions per second, N(N-1)/t, particle state already 
 e2e    = same metric through the reference-facing call with HOST buffers (H2D of x, m and D2H of a
          inside the timed region): at N=1 literally the drop-in `acceleration()` symbol
 Also reported on the same line: roofline (FP64 pipe), cpu_baseline (compiled reference on the host, bounded
-sample), Barnes-Hut force-evaluation time ("bh"), clocks, gpu_launches.
+sample), clocks, gpu_launches, a sampled parity check against the reference arithmetic ("parity"), and -- inside
+`config`, which the driver's parser keeps whole -- the second half of BASELINE.json's metric: Barnes-Hut full
+force evaluation, s per step, at N = 2^24 (the north-star size) and 2^20, Plummer and uniform, theta = 0.5, with its
+own cpu_baseline (the reference's OpenMP walk on the host cores), end-to-end time through acceleration_barnes_hut()
+with host buffers, per-stage times and HBM-roofline fractions.
 """
 from __future__ import annotations
 
@@ -50,7 +54,9 @@ def parse_args():
     p.add_argument("--n", type=int, default=1 << 20, help="particles of the direct-sum workload")
     p.add_argument("--eps", type=float, default=0.01)
     p.add_argument("--ic", default="plummer", choices=["plummer", "uniform"])
-    p.add_argument("--bh-n", type=int, default=1 << 20, help="particles of the Barnes-Hut side measurement (0 = skip)")
+    p.add_argument("--bh-n", type=int, default=1 << 24, help="largest Barnes-Hut size (north star: 2^24; 0 = skip); 2^20 is always the second point")
+    p.add_argument("--bh-cpu-n", type=int, default=1 << 20, help="particles of the Barnes-Hut CPU baseline (reference, OpenMP; 0 = skip)")
+    p.add_argument("--no-parity", action="store_true")
     p.add_argument("--whfast-n", type=int, default=100000,
                    help="massless asteroids of the WHFast side measurement (config 3; 0 = skip; single GPU only)")
     p.add_argument("--cpu-n", type=int, default=1 << 16, help="particles of the bounded CPU-baseline sample (0 = skip)")
@@ -156,13 +162,17 @@ def run_reference_arm(args):
         impl.acceleration(x, m, G, "pairwise", args.eps)
     dt = (time.perf_counter() - t0) / args.steps
     val = n * (n - 1) / dt / 1e9
-    sample = (f"pairwise force evaluation of the first-principles same workload at N={n} ({args.ic}, eps={args.eps}); "
-              f"interactions/s is size-independent for the O(N^2) loop; full N={args.n} would take ~{dt * (args.n / n) ** 2 / 60:.0f} min")
+    sample = (f"pairwise force evaluation at N={n} ({args.ic}, eps={args.eps}), the largest size whose {args.steps}+{args.warmup} "
+              f"evaluations fit the few-minute budget on one core; interactions/s is size-independent for the O(N^2) loop")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"direct-sum pairwise FP64, {args.ic} N={args.n}, eps={args.eps} (timed on a bounded sample N={n})"},
+        # the workload named here is the one actually timed; the b200 arm's N is reported separately
+        "config": {"workload": f"direct-sum pairwise FP64 force evaluation, {args.ic} N={n}, eps={args.eps}",
+                   "b200_arm_n": args.n,
+                   "extrapolated_ms_per_step_at_b200_arm_n": dt * 1e3 * (args.n / n) ** 2,
+                   "threads": "1 (src/acceleration.c has no OpenMP in the pairwise loop)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kname, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -172,6 +182,129 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
+
+
+# ---------------------------------------------------------------------------------------------------------
+# checkers and the Barnes-Hut half of the metric
+# ---------------------------------------------------------------------------------------------------------
+
+def direct_sum_parity(x, m, G, eps, a, k=256):
+    """max relative error of k sampled rows of `a` against the reference's operation order for those targets
+    (oracle.pairwise_targets, pinned bit-equal to the compiled reference in tests/test_oracle.py)."""
+    from oracle.bind import Oracle
+    n = m.shape[0]
+    r = np.linalg.norm(x, axis=1)
+    tg = np.unique(np.concatenate([np.argsort(r)[:32], np.random.default_rng(5).choice(n, min(k, n), replace=False)])).astype(np.int32)
+    ref = Oracle().pairwise_targets(x, m, G, eps, tg)
+    err = float(np.max(np.linalg.norm(a[tg] - ref, axis=1) / np.linalg.norm(ref, axis=1)))
+    return {"what": f"direct sum N={n}: {tg.shape[0]} sampled targets x all sources vs the reference's summation order (CPU oracle)",
+            "max_rel": err, "tol": 1e-12, "ok": bool(err <= 1e-12)}
+
+
+BH_STAGE_BYTES = {"bbox_morton": 60.0, "sort": 204.0, "build": 79.0, "walk": 127.0}   # SURVEY.md section 8d, per particle
+
+
+def _ncu_bh_traffic():
+    """per-launch DRAM bytes of the BH stages from the committed ncu captures (profiles/r2_bh_dram_bytes.json), if present"""
+    try:
+        return json.load(open(ROOT / "profiles" / "r2_bh_dram_bytes.json"))
+    except Exception:
+        return None
+
+
+def run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks):
+    from oracle.bind import Oracle, Reference
+    theta, leaf, eps = 0.5, 1, args.eps
+    sizes = sorted({args.bh_n, min(args.bh_n, 1 << 20)}, reverse=True)
+    runs = []
+    parity = None
+    traffic = _ncu_bh_traffic()
+    for n in sizes:
+        for ic in ("plummer", "uniform"):
+            x, v, m, G = make_ic(ic, n, seed=43)
+            ctx.set_system(x, m, G, v)
+            for _ in range(2):
+                ctx.mark_positions_sharded()
+                ctx.acceleration("barnes_hut", eps, theta, leaf)
+            ctx.synchronize()
+            barrier()
+            tt, stages = [], []
+            for _ in range(3):
+                ctx.flush_l2()
+                ctx.mark_positions_sharded()
+                ctx.event_record(2)
+                ctx.acceleration("barnes_hut", eps, theta, leaf)
+                ctx.event_record(3)
+                tt.append(ctx.event_elapsed_ms(2, 3))
+                stages.append([ctx.timing_ms(s) for s in (1, 3, 4, 5, 2)])
+            ms = max_over_ranks(float(np.mean(tt)))
+            st = np.mean(np.array(stages), axis=0)
+            run = {"n": n, "ic": ic, "value": ms * 1e-3, "unit": "s",
+                   "stage_ms": {"gather": st[0], "bbox_morton": st[1], "sort": st[2], "build": st[3], "walk": st[4]},
+                   "hbm_frac_algorithmic": (470.0 * n / (ms * 1e-3) / 1e9) / _hbm_peak(),
+                   "stage_hbm_frac": {k: (b * n / (max(t_ms, 1e-6) * 1e-3) / 1e9) / _hbm_peak()
+                                      for (k, b), t_ms in zip(BH_STAGE_BYTES.items(), st[1:])}}
+            if traffic and traffic.get("n") == n and traffic.get("ic") == ic and world == 1:
+                run["ncu_dram_bytes_per_stage"] = traffic["stages"]
+            # sampled parity + items/s at the size the CPU port builds in under a second
+            a_all = ctx.accelerations()
+            if rank == 0 and n <= (1 << 20) and not args.no_parity:
+                with Oracle().tree(x, m, leaf) as T:
+                    starts = np.random.default_rng(0).choice(n // 32, min(64, n // 32), replace=False) * 32
+                    pos = (starts[:, None] + np.arange(32)[None, :]).ravel()
+                    ref, stats = T.walk_targets(G, eps, theta, pos, stats=True)
+                    ids = T.to_dict()["sorted_indices"][pos]
+                err = float(np.max(np.linalg.norm(a_all[ids] - ref, axis=1) / np.linalg.norm(ref, axis=1)))
+                items = float(stats[:, 0].mean() + stats[:, 3].mean())
+                run["items_per_target_sampled"] = items
+                run["items_per_s"] = items * n / (st[4] * 1e-3)     # node visits + leaf particles of all targets per second of walk
+                run["parity"] = {"what": f"{pos.shape[0]} sampled targets vs the CPU port of the reference walk (bit-pinned to the compiled reference)",
+                                 "max_rel": err, "tol": 1e-12, "ok": bool(err <= 1e-12)}
+                parity = run["parity"] if parity is None or not run["parity"]["ok"] else parity
+            # end to end through the reference-facing call with HOST buffers
+            if not args.no_e2e:
+                a_host = np.empty((n, 3))
+                if world == 1:
+                    f = lambda: gb.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)     # drop-in acceleration() symbol
+                    api = "acceleration() [method = barnes_hut] in libgrav_sim_b200.so"
+                else:
+                    def f():
+                        ctx.set_system(x, m, G)
+                        ctx.acceleration("barnes_hut", eps, theta, leaf)
+                        return ctx.accelerations(a_host)
+                    api = "grav_b200_ctx_set_system/_acceleration/_get_accelerations"
+                f()
+                barrier()
+                t0 = time.perf_counter()
+                out = f()
+                barrier()
+                e2e_s = max_over_ranks(time.perf_counter() - t0)
+                run["e2e"] = {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(x.nbytes + m.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                              "api": api}
+            runs.append(run)
+    # CPU baseline: the compiled reference, OpenMP walk on all host cores (its build phase is serial)
+    cpu = None
+    if rank == 0 and args.bh_cpu_n > 0:
+        impl, kname = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
+        cpu = {"unit": "s", "cores": os.cpu_count() if kname == "reference" else 1, "kind": kname, "n": args.bh_cpu_n, "runs": []}
+        for ic in ("plummer", "uniform"):
+            x, v, m, G = make_ic(ic, args.bh_cpu_n, seed=43)
+            t0 = time.perf_counter()
+            impl.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)
+            cpu["runs"].append({"ic": ic, "value": time.perf_counter() - t0})
+        cpu["value"] = cpu["runs"][0]["value"]
+        cpu["sample"] = (f"one acceleration_barnes_hut() call of the {'compiled reference (OpenMP walk, serial tree build)' if kname == 'reference' else 'C port (serial)'} "
+                         f"at N={args.bh_cpu_n}, theta={theta}, {cpu['cores']} host threads; value = plummer")
+    head = runs[0]
+    return {"metric": "barnes_hut_force_eval_s_per_step", "value": head["value"], "unit": "s", "higher_is_better": False,
+            "workload": f"Barnes-Hut full force evaluation (bbox, Morton keys, sort, octree + moments, walk), plummer N={head['n']}, theta={theta}, "
+                        f"leaf={leaf}, eps={eps}; reference walk semantics, cooperative walk kernel (<= 1e-12 vs the reference)",
+            "n_gpus": world, "scaling": "strong", "partition": "replicated build, walk sharded in interleaved 2048-position chunks, all-gather of the results" if world > 1 else "single GPU",
+            "runs": runs, "cpu_baseline": cpu, "parity": parity,
+            "stage_bytes_per_particle": BH_STAGE_BYTES,
+            "roofline_note": "north_star names the HBM roofline for sort/build/walk: stage_hbm_frac = SURVEY 8d algorithmic bytes / stage time / measured HBM peak; "
+                             "the walk is L2-latency / issue bound (L2 hit rate 99.8 %, profiles/r2_walk_coop_*.txt), items_per_s is its figure of merit"}
+
 
 def run_b200_arm(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -302,37 +435,18 @@ def run_b200_arm(args):
                "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": e2e_s * 1e3,
                "api": "acceleration() in libgrav_sim_b200.so" if world == 1 else "grav_b200_ctx_set_system/_acceleration/_get_accelerations"}
 
-    # Barnes-Hut side measurement (second half of the metric): s per full force evaluation
+    # sampled parity of what was just timed, against the reference's arithmetic (checker only, outside every timed region)
+    parity = None
+    if not args.no_parity:
+        a_all = ctx.accelerations()
+        if rank == 0:
+            parity = direct_sum_parity(x, m, G, args.eps, a_all)
+
+    # Barnes-Hut (second half of the metric): s per full force evaluation, theta = 0.5, leaf = 1
     bh = None
     if args.bh_n > 0:
         try:
-            xb, vb, mb, Gb = make_ic(args.ic, args.bh_n, seed=43)
-            ctx.set_system(xb, mb, Gb, vb)
-            for _ in range(2):
-                ctx.mark_positions_sharded()
-                ctx.acceleration("barnes_hut", args.eps, 0.5, 1)
-            ctx.synchronize()
-            barrier()
-            tt, stages = [], []
-            for _ in range(3):
-                ctx.flush_l2()
-                ctx.mark_positions_sharded()
-                ctx.event_record(2)
-                ctx.acceleration("barnes_hut", args.eps, 0.5, 1)
-                ctx.event_record(3)
-                tt.append(ctx.event_elapsed_ms(2, 3))
-                stages.append([ctx.timing_ms(s) for s in (1, 3, 4, 5, 2)])
-            bh_ms = max_over_ranks(float(np.mean(tt)))
-            st = np.mean(np.array(stages), axis=0)
-            bh = {"metric": "barnes_hut_force_eval_s_per_step", "value": bh_ms * 1e-3, "unit": "s", "n": args.bh_n,
-                  "theta": 0.5, "leaf": 1, "ic": args.ic, "mode": "reference-exact",
-                  "stage_ms": {"gather": st[0], "bbox_morton": st[1], "sort": st[2], "build": st[3], "walk": st[4]},
-                  "hbm_frac_algorithmic": (470.0 * args.bh_n / (bh_ms * 1e-3) / 1e9) / _hbm_peak(),
-                  # algorithmic bytes per particle of each stage over the stage time and the HBM peak
-                  "stage_hbm_frac": {k: (b * args.bh_n / (max(t_ms, 1e-6) * 1e-3) / 1e9) / _hbm_peak()
-                                     for k, b, t_ms in (("bbox_morton", 60.0, st[1]), ("sort", 204.0, st[2]),
-                                                        ("build", 79.0, st[3]), ("walk", 127.0, st[4]))},
-                  "stage_bytes_per_particle": {"bbox_morton": 60, "sort": 204, "build": 79, "walk": 127}}
+            bh = run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks)
         except gb.GravB200Error as e:
             bh = {"unavailable": str(e)[:200]}
 
@@ -407,9 +521,12 @@ def run_b200_arm(args):
             "data": "synthetic",
             "config": {"workload": f"direct-sum pairwise FP64 force evaluation, {args.ic} N={n}, eps={args.eps}",
                        "partition": f"targets sharded over {world} rank(s), NCCL all-gather of positions per step" if world > 1 else "single GPU",
-                       "l2": "256 MiB L2 flush between timed iterations"},
+                       "l2": "256 MiB L2 flush between timed iterations",
+                       # second half of BASELINE.json's metric ("... & BH force-eval s/step"): kept inside config so the
+                       # driver's parser, which keeps config whole, carries it into BENCH / SCALE
+                       "barnes_hut": bh},
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "bh": bh, "massless": ml, "whfast": wh, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "massless": ml, "whfast": wh, "gpu_launches": int(launches),
             "clocks": clocks, "allgather_ms": float(np.mean(gather_ms)) if world > 1 else 0.0,
         }
         print(json.dumps(line), flush=True)

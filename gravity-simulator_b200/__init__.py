@@ -96,7 +96,8 @@ ABI_SYMBOLS = [
     "grav_b200_acceleration_massless", "grav_b200_acceleration_barnes_hut",
     "grav_b200_whfast_acceleration_pairwise", "grav_b200_whfast_acceleration_massless",
     "grav_b200_construct_octree", "grav_b200_morton_keys", "grav_b200_set_bh_mode", "grav_b200_get_bh_mode",
-    "grav_b200_set_bh_exact", "grav_b200_get_bh_exact",
+    "grav_b200_set_bh_exact", "grav_b200_get_bh_exact", "grav_b200_ctx_create_team", "grav_b200_ctx_create_auto",
+    "grav_b200_ctx_team_size",
     "grav_b200_ctx_create", "grav_b200_ctx_destroy", "grav_b200_nccl_unique_id", "grav_b200_ctx_set_system",
     "grav_b200_ctx_set_positions", "grav_b200_ctx_num_particles", "grav_b200_ctx_owned_range",
     "grav_b200_ctx_acceleration", "grav_b200_ctx_get_positions", "grav_b200_ctx_get_velocities",
@@ -138,6 +139,9 @@ def load():
     abi.grav_b200_ctx_owned_range.restype = None
     abi.grav_b200_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]
     abi.grav_b200_ctx_destroy.argtypes = [C.c_void_p]
+    abi.grav_b200_ctx_create_team.argtypes = [C.POINTER(C.c_void_p), C.c_int, c_int_p]
+    abi.grav_b200_ctx_create_auto.argtypes = [C.POINTER(C.c_void_p)]
+    abi.grav_b200_ctx_team_size.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_set_system.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double]
     abi.grav_b200_ctx_set_positions.argtypes = [C.c_void_p, c_double_p]
     abi.grav_b200_ctx_num_particles.argtypes = [C.c_void_p]
@@ -334,12 +338,21 @@ def device_count() -> int:
 class Context:
     """Device-resident particle state (include/grav_b200.h, family 2)."""
 
-    def __init__(self, device=0, rank=0, world_size=1, nccl_unique_id: bytes | None = None):
+    def __init__(self, device=0, rank=0, world_size=1, nccl_unique_id: bytes | None = None, team=None):
+        """team: list of device ids (or a count) -> an in-process device team led by this object (grav_b200_ctx_create_team)."""
         self.abi, _ = load()
         self.h = C.c_void_p()
-        uid = C.create_string_buffer(nccl_unique_id, 128) if nccl_unique_id is not None else None
-        check_rc(self.abi.grav_b200_ctx_create(C.byref(self.h), device, rank, world_size, uid))
+        if team is not None:
+            devs = list(range(team)) if isinstance(team, int) else list(team)
+            arr = (C.c_int * len(devs))(*devs)
+            check_rc(self.abi.grav_b200_ctx_create_team(C.byref(self.h), len(devs), arr))
+        else:
+            uid = C.create_string_buffer(nccl_unique_id, 128) if nccl_unique_id is not None else None
+            check_rc(self.abi.grav_b200_ctx_create(C.byref(self.h), device, rank, world_size, uid))
         self.n = 0
+
+    def team_size(self) -> int:
+        return int(self.abi.grav_b200_ctx_team_size(self.h))
 
     @staticmethod
     def new_unique_id() -> bytes:

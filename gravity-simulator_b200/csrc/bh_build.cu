@@ -209,14 +209,13 @@ __global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *__restrict__ re
                 const int ps = rec[r.parent].b[0], pss = rec[r.parent].same_start;
                 id = 1 + P[ps] + pss + r.rank;
             } else {
-                topo[0].next = -1; topo[0].first = 0; topo[0].level_count = n;   // root: level 0
+                topo[0].next = -1; topo[0].first = 0; topo[0].shift_count = (unsigned)n;   // root (never tested: shift and cell2 unused)
+                topo[0].cell2 = 0.0;
                 geo[0].kq = 0;
             }
             rec[u].first_child = fcu;
             rec[u].id = id;
-            topo[id].fc = fcu;
-            topo[id].nch = r.nch;
-            topo[id].pad = 0;
+            topo[id].fcn = ((unsigned)fcu << 4) | (unsigned)r.nch;
         }
         if (k < r.nch) {
             const int cid = fcu + k, first = r.b[k], cnt = r.b[k + 1] - first;
@@ -236,10 +235,11 @@ __global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *__restrict__ re
             WalkTopo *w = topo + cid;
             w->next = nxt;
             w->first = first;
-            w->level_count = (cl << WALK_COUNT_BITS) | cnt;
+            w->shift_count = ((unsigned)(3 * (MAX_LEVEL - cl)) << WALK_COUNT_BITS) | (unsigned)cnt;
+            w->cell2 = meta->cell2[cl];
             geo[cid].kq = fixed_mode ? K[first] : K[perm[first]];
             if (!(cnt > max_leaf && cl < MAX_LEVEL)) {   // stays a leaf
-                w->fc = -1; w->nch = 0; w->pad = 0;
+                w->fcn = 0;
                 w->mass = 0.0;
                 geo[cid].cx = 0.0; geo[cid].cy = 0.0; geo[cid].cz = 0.0;
             }
@@ -328,10 +328,10 @@ __global__ void __launch_bounds__(256) export_nodes_kernel(int M, const WalkGeo 
     if (id >= M) return;
     const WalkTopo w = topo[id];
     const WalkGeo g = geo[id];
-    np[id] = w.level_count & COUNT_MASK;
-    nchild[id] = w.nch;
+    np[id] = (int)(w.shift_count & (unsigned)COUNT_MASK);
+    nchild[id] = (int)(w.fcn & 15u);
     first[id] = w.first;
-    fc[id] = w.fc;              // -1 for leaves (the reference leaves it uninitialised)
+    fc[id] = (w.fcn & 15u) ? (int)(w.fcn >> 4) : -1;   // -1 for leaves (the reference leaves it uninitialised)
     mass[id] = w.mass;
     cx[id] = g.cx; cy[id] = g.cy; cz[id] = g.cz;
 }

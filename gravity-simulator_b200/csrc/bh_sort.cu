@@ -738,40 +738,56 @@ int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, in
     DevTree &t = c->tree;
     constexpr int TILE = SORT_THREADS * SORT_ROUNDS_SMALL;
     const int num_tiles = (n + TILE - 1) / TILE;
-    // Both kernels below wait for every tile of the grid, so the whole grid has to be resident at once.  True for
-    // <= 128 CTAs on a full B200 (148 SMs x >= 2 CTAs); on anything smaller (a MIG slice) fall back to the
-    // histogram + scatter pair of launches per pass, which has no inter-CTA waits.
-    static int resident_ctas = -1;
-    if (resident_ctas < 0) {
+    // Both kernels below wait for every tile of the grid, so the whole grid has to be resident at once.  They are
+    // launched COOPERATIVELY: the runtime then either places all CTAs together or refuses the launch, and it never
+    // interleaves two cooperative grids half-resident (two contexts or streams sorting on the same GPU at the same time
+    // cannot starve each other).  A refusal, or a device too small for the grid (a MIG slice), falls back to the
+    // histogram + scatter pair of launches per pass, which has no inter-CTA waits.  The residency estimate is kept per
+    // context: it depends on the device.
+    if (c->sort_resident_ctas < 0) {
         int per_sm_all = 0, per_sm_pass = 0;
         GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_all, sort_small_all_kernel<SORT_ROUNDS_SMALL>, SORT_THREADS, 0));
         GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pass, sort_small_pass_kernel<SORT_ROUNDS_SMALL>, SORT_THREADS, 0));
-        resident_ctas = c->sm_count * (per_sm_all < per_sm_pass ? per_sm_all : per_sm_pass);
+        c->sort_resident_ctas = c->sm_count * (per_sm_all < per_sm_pass ? per_sm_all : per_sm_pass);
     }
-    if (num_tiles > resident_ctas) {
+    auto wait_free_passes = [&]() -> int {
         for (int pass = 0; pass < 8; pass++) {
             GB_TRY(radix_pass(c, ka, pa, kb, pb, n, pass * SORT_BITS));
             long long *tk = ka; ka = kb; kb = tk;
             int *tp = pa; pa = pb; pb = tp;
         }
         return GRAV_B200_OK;
-    }
+    };
+    if (num_tiles > c->sort_resident_ctas) return wait_free_passes();
     const size_t words = (size_t)8 * SMALL_MAX_TILES * SORT_RADIX + 8;      // 1 MiB of status words + 8 barrier counters
     GB_TRY(t.hist.reserve(sizeof(int) * words));
     unsigned *status = t.hist.as<unsigned>();
     GB_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * words, c->stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)num_tiles);
+    cfg.blockDim = dim3(SORT_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute coop[1];
+    coop[0].id = cudaLaunchAttributeCooperative;
+    coop[0].val.cooperative = 1;
+    cfg.attrs = coop;
+    cfg.numAttrs = 1;
     static const bool per_pass = getenv("GRAV_B200_SORT_SMALL_PER_PASS") && atoi(getenv("GRAV_B200_SORT_SMALL_PER_PASS")) != 0;
     if (!per_pass) {
-        sort_small_all_kernel<SORT_ROUNDS_SMALL><<<num_tiles, SORT_THREADS, 0, c->stream>>>(ka, pa, kb, pb, n, num_tiles, status,
-                                                                                           status + words - 8);
-        GB_LAUNCH_CHECK();
+        unsigned *barrier = status + words - 8;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, sort_small_all_kernel<SORT_ROUNDS_SMALL>, ka, pa, kb, pb, n, num_tiles, status, barrier);
+        if (e == cudaErrorCooperativeLaunchTooLarge) { cudaGetLastError(); return wait_free_passes(); }
+        GB_CUDA(e);
         count_launch();
         return GRAV_B200_OK;        // even number of passes: the result is in ka / pa
     }
     for (int pass = 0; pass < 8; pass++) {
-        sort_small_pass_kernel<SORT_ROUNDS_SMALL><<<num_tiles, SORT_THREADS, 0, c->stream>>>(ka, pa, n, pass * SORT_BITS, num_tiles,
-                                                                                            status + (size_t)pass * SMALL_MAX_TILES * SORT_RADIX, kb, pb);
-        GB_LAUNCH_CHECK();
+        unsigned *st = status + (size_t)pass * SMALL_MAX_TILES * SORT_RADIX;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, sort_small_pass_kernel<SORT_ROUNDS_SMALL>, (const long long *)ka, (const int *)pa, n,
+                                                 pass * SORT_BITS, num_tiles, st, kb, pb);
+        if (e == cudaErrorCooperativeLaunchTooLarge && pass == 0) { cudaGetLastError(); return wait_free_passes(); }
+        GB_CUDA(e);
         count_launch();
         long long *tk = ka; ka = kb; kb = tk;
         int *tp = pa; pa = pb; pb = tp;
@@ -787,10 +803,9 @@ int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long
     constexpr int TILE_BIG = SORT_THREADS * SORT_ROUNDS, TILE_SMALL = SORT_THREADS * SORT_ROUNDS_SMALL;
     constexpr size_t SMEM_BIG = (size_t)TILE_BIG * (sizeof(long long) + sizeof(int));       // staging: 48 KiB
     constexpr size_t SMEM_SMALL = (size_t)TILE_SMALL * (sizeof(long long) + sizeof(int));   // 12 KiB
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->sort_attr_scatter) {    // per device, hence per context
         GB_CUDA(cudaFuncSetAttribute(sort_scatter_kernel<SORT_ROUNDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BIG));
-        attr_set = true;
+        c->sort_attr_scatter = true;
     }
     if (n <= SORT_SMALL_MAX_N) {
         const int num_tiles = (n + TILE_SMALL - 1) / TILE_SMALL;
@@ -823,10 +838,9 @@ static int onesweep_sort_t(grav_b200_ctx *c, long long *ka, int *pa, long long *
     DevTree &t = c->tree;
     constexpr int TILE = SORT_THREADS * ROUNDS;
     constexpr size_t SMEM = (size_t)TILE * (sizeof(long long) + sizeof(int));
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->sort_attr_onesweep) {   // per device, hence per context
         GB_CUDA(cudaFuncSetAttribute(sort_onesweep_kernel<ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_set = true;
+        c->sort_attr_onesweep = true;
     }
     const int num_tiles = (n + TILE - 1) / TILE;
     // scratch layout (ints): [0, 2048) digit totals of the 8 passes, [2048, 2056) tickets, then 8 x num_tiles x 256 status words

@@ -66,15 +66,15 @@ __device__ __forceinline__ void ldg256(const void *p, long long &a, long long &b
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
-struct NodeRec {   // a node's two records as two 256-bit loads (the mass rides along: no third load on accept)
+struct NodeRec {   // a node's two records as two 256-bit loads (mass and cell size ride along: no third load)
     long long cx, cy, cz, kq;   // raw bits
-    long long fc_next, first_lc, mass, nch_pad;
+    long long fcn_next, first_sc, mass, cell2;
 };
-__device__ __forceinline__ NodeRec load_rec(const WalkGeo *geo, const WalkTopo *topo, int node)
+__device__ __forceinline__ NodeRec load_rec(const WalkGeo *geo, const WalkTopo *topo, unsigned node)
 {
     NodeRec r;
     ldg256(geo + node, r.cx, r.cy, r.cz, r.kq);
-    ldg256(topo + node, r.fc_next, r.first_lc, r.mass, r.nch_pad);
+    ldg256(topo + node, r.fcn_next, r.first_sc, r.mass, r.cell2);
     return r;
 }
 
@@ -103,31 +103,45 @@ __device__ __forceinline__ void eval_fast(double sx, double sy, double sz, doubl
 // ---------------------------------------------------------------------------------------------------------------------
 // warp-cooperative walk
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int CW_WARPS = 4;       // warps per CTA
+#ifndef CW_WARPS_DEF
+#define CW_WARPS_DEF 4
+#endif
+#ifndef CW_SYNC
+#define CW_SYNC 0
+#endif
+constexpr int CW_WARPS = CW_WARPS_DEF;       // warps per CTA
 constexpr int CW_STACK = 512;     // stack entries per warp (4 bytes each: first child id << 4 | number of children)
 // Above CW_HIGH entries the warp pops ONE opened node per trip, i.e. walks depth-first, where the stack grows by at most
 // 7 entries per level, 140 in all; four at a time it grows by at most 28 per trip.  320 + 28 + 140 < 512.
 constexpr int CW_HIGH = 320;
 
+#ifndef CW_MINB
+#define CW_MINB 8     // 64 registers, 32 warps per SM: the walk is latency bound (8 CTAs 18.9 ms, 6 CTAs / 80 registers 22.9 ms at N = 2^20 Plummer)
+#endif
+
 template <bool FIXED>
-__global__ void __launch_bounds__(CW_WARPS * 32, 8) walk_coop_kernel(const WalkArgs a, int tpw, long long slots)
+__global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) walk_coop_kernel(const WalkArgs a, int tpw, long long slots)
 {
-    __shared__ double s_cell2[MAX_LEVEL + 3];
     __shared__ unsigned s_stack[CW_WARPS][CW_STACK];
-    if (threadIdx.x < MAX_LEVEL + 1) s_cell2[threadIdx.x] = a.meta->cell2[threadIdx.x];
-    __syncthreads();
     if (a.meta->overflow) return;   // the build did not fit its buffers: the planes are not a tree (reported by the host)
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned *stk = s_stack[wib];
-    const int e = lane >> 3, k = lane & 7;
+    const int lane = threadIdx.x & 31;
+    unsigned *const stk = s_stack[threadIdx.x >> 5];
+    const int e = lane >> 3;
+    const unsigned k = lane & 7;
     const unsigned lt = (1u << lane) - 1u;
-    const int root_fc = __ldg(&a.topo[0].fc), root_nch = __ldg(&a.topo[0].nch);   // the root is always expanded
-    const long long t0 = ((long long)blockIdx.x * CW_WARPS + wib) * tpw;
+    const unsigned root_ent = __ldg(&a.topo[0].fcn);   // the root is always expanded
+    const long long t0 = ((long long)blockIdx.x * CW_WARPS + (threadIdx.x >> 5)) * tpw;
     for (int tt = 0; tt < tpw; tt++) {
         const long long t = t0 + tt;                     // slot of this rank
-        if (t >= slots) break;
         const long long q = slot_to_position(a, t);
-        if (q >= a.n) break;                             // positions grow with the slot
+        if (t >= slots || q >= a.n) {                    // positions grow with the slot: nothing further for this warp
+#if CW_SYNC
+            __syncthreads();
+            continue;
+#else
+            break;
+#endif
+        }
         const int p = (int)q;
         const int idx = __ldg(&a.perm[p]);
         long long mx, my, mz, mw;
@@ -137,46 +151,43 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 8) walk_coop_kernel(const WalkA
         double ax = 0.0, ay = 0.0, az = 0.0;
 
         int sp = 0;
-        int fc = (e == 0) ? root_fc : 0;
-        int nch = (e == 0) ? root_nch : 0;
-        bool active = k < nch;
+        unsigned ent = (e == 0) ? root_ent : 0u;
+        bool active = k < (ent & 15u);
         NodeRec rec = {};
-        if (active) rec = load_rec(a.geo, a.topo, fc + k);
+        if (active) rec = load_rec(a.geo, a.topo, (ent >> 4) + k);
         for (;;) {
             bool open = false, have = false;
             int lf_first = 0, lf_count = 0;
-            double sx = 0.0, sy = 0.0, sz = 0.0, sm = 0.0;
+            double dx = 0.0, dy = 0.0, dz = 0.0, d2 = 0.0, sm = 0.0;   // source minus target, squared distance, source mass
             unsigned child_ent = 0;
             if (active) {
-                const double cx = __longlong_as_double(rec.cx), cy = __longlong_as_double(rec.cy), cz = __longlong_as_double(rec.cz);
-                const int cfc = (int)rec.fc_next;
-                const int lc = (int)(rec.first_lc >> 32);
-                const int level = lc >> WALK_COUNT_BITS;
-                const bool leaf = cfc < 0;
-                const bool inside = ((ki ^ rec.kq) >> (3 * (MAX_LEVEL - level))) == 0;
-                // the decision arithmetic of src/acceleration_barnes_hut.c:150-162, operation for operation
-                const double rx = __dsub_rn(xi, cx), ry = __dsub_rn(yi, cy), rz = __dsub_rn(zi, cz);
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                const bool far = s_cell2[level] < __dmul_rn(a.theta2, d2);
+                sm = __longlong_as_double(rec.mass);
+                child_ent = (unsigned)rec.fcn_next;
+                const unsigned sc = (unsigned)(rec.first_sc >> 32);
+                const bool leaf = (child_ent & 15u) == 0u;
+                const bool inside = ((unsigned long long)(ki ^ rec.kq) >> (sc >> WALK_COUNT_BITS)) == 0ull;
+                // the decision arithmetic of src/acceleration_barnes_hut.c:150-162, operation for operation (the reference
+                // forms x_i - com; com - x_i is its exact negative, so the squares and their sum are the same doubles)
+                dx = __dsub_rn(__longlong_as_double(rec.cx), xi);
+                dy = __dsub_rn(__longlong_as_double(rec.cy), yi);
+                dz = __dsub_rn(__longlong_as_double(rec.cz), zi);
+                d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                const bool far = __longlong_as_double(rec.cell2) < __dmul_rn(a.theta2, d2);
                 const bool accepted = FIXED ? (!inside && !leaf && far) : (!inside && far);
-                if (accepted) {
-                    sm = __longlong_as_double(rec.mass);
-                    have = sm != 0.0;             // d2 > 0 here, so a zero-mass node (a dropped leaf) contributes exactly 0
-                    sx = cx; sy = cy; sz = cz;
-                } else if (leaf) {
-                    lf_first = (int)rec.first_lc;
-                    lf_count = lc & COUNT_MASK;
-                } else {
-                    open = true;
-                    child_ent = ((unsigned)cfc << 4) | (unsigned)(int)rec.nch_pad;
+                open = !accepted && !leaf;
+                have = accepted && sm != 0.0;      // d2 > 0 here, so a zero-mass node (a dropped leaf) contributes exactly 0
+                if (!accepted && leaf) {
+                    lf_first = (int)rec.first_sc;
+                    lf_count = (int)(sc & (unsigned)COUNT_MASK);
+                    if (lf_first != p) {          // first (usually only) particle of the leaf: same path as an accepted node
+                        long long qx, qy, qz, qw;
+                        ldg256(a.psorted + lf_first, qx, qy, qz, qw);
+                        dx = __longlong_as_double(qx) - xi; dy = __longlong_as_double(qy) - yi; dz = __longlong_as_double(qz) - zi;
+                        d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                        sm = __longlong_as_double(qw);
+                        have = true;
+                    }
                 }
-            }
-            if (lf_count > 0 && lf_first != p) {      // first (usually only) particle of a leaf: same path as an accepted node
-                long long qx, qy, qz, qw;
-                ldg256(a.psorted + lf_first, qx, qy, qz, qw);
-                sx = __longlong_as_double(qx); sy = __longlong_as_double(qy); sz = __longlong_as_double(qz);
-                sm = __longlong_as_double(qw);
-                have = true;
             }
             const unsigned om = __ballot_sync(0xffffffffu, open);
             if (open) stk[sp + __popc(om & lt)] = child_ent;
@@ -184,17 +195,19 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 8) walk_coop_kernel(const WalkA
             __syncwarp();
             // next batch: its record loads are in flight while this trip's sources are evaluated
             const bool more = sp > 0;
-            if (more) {
-                const int take = sp > CW_HIGH ? 1 : min(sp, 4);
-                const unsigned ent = (e < take) ? stk[sp - 1 - e] : 0u;
-                __syncwarp();
-                sp -= take;
-                fc = (int)(ent >> 4);
-                nch = (int)(ent & 15u);
-                active = k < nch;
-                if (active) rec = load_rec(a.geo, a.topo, fc + k);
+            const int take = sp > CW_HIGH ? 1 : min(sp, 4);       // 0 when the stack is empty: every lane goes idle
+            ent = stk[max(sp - 1 - e, 0)];
+            if (e >= take) ent = 0u;
+            __syncwarp();
+            sp -= take;
+            active = k < (ent & 15u);
+            if (active) rec = load_rec(a.geo, a.topo, (ent >> 4) + k);
+            if (have) {                                // the separation is already there: m r^-3 and three FMAs
+                const double s = inv_r3_times_m(d2 + a.eps2, sm);
+                ax = fma(s, dx, ax);
+                ay = fma(s, dy, ay);
+                az = fma(s, dz, az);
             }
-            if (have) eval_fast(sx, sy, sz, sm, xi, yi, zi, a.eps2, ax, ay, az);
             if (lf_count > 1) {                       // max_leaf > 1, or duplicates at level 21: the rest of the leaf
                 for (int j = 1; j < lf_count; j++) {
                     const int pos = lf_first + j;
@@ -218,7 +231,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 8) walk_coop_kernel(const WalkA
             if (a.out_slots) a.out_slots[3 * (size_t)t + lane] = v;
             else a.acc[3 * (size_t)idx + lane] = v;
         }
+#if CW_SYNC
+        __syncthreads();     // keeps the CTA's warps on neighbouring targets in phase (they stream the same nodes through L1)
+#else
         __syncwarp();
+#endif
     }
 }
 
@@ -235,9 +252,6 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 8) walk_coop_kernel(const WalkA
 template <bool FIXED, bool EXACT>
 __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkArgs a, long long slots)
 {
-    __shared__ double s_cell2[MAX_LEVEL + 3];
-    if (threadIdx.x < MAX_LEVEL + 1) s_cell2[threadIdx.x] = a.meta->cell2[threadIdx.x];
-    __syncthreads();
     if (a.meta->overflow) return;
     const long long t = (long long)blockIdx.x * WALK_BLOCK + threadIdx.x;
     if (t >= slots) return;
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
     const long long ki = FIXED ? a.K[p] : a.K[idx];
     double ax = 0.0, ay = 0.0, az = 0.0;
 
-    int node = __ldg(&a.topo[0].fc);   // the root is always expanded
+    int node = (int)(__ldg(&a.topo[0].fcn) >> 4);   // the root is always expanded
     NodeRec rec = load_rec(a.geo, a.topo, node);
     int leaf_pos = 0, leaf_rem = 0, leaf_next = -1;
     while (node >= 0) {
@@ -262,17 +276,17 @@ __global__ void __launch_bounds__(WALK_BLOCK, WALK_MINB) walk_kernel(const WalkA
         if (leaf_rem == 0) {
             const double cx = __longlong_as_double(rec.cx), cy = __longlong_as_double(rec.cy), cz = __longlong_as_double(rec.cz);
             const long long kq = rec.kq;
-            const int fc = (int)rec.fc_next, next = (int)(rec.fc_next >> 32), first = (int)rec.first_lc;
-            const int lc = (int)(rec.first_lc >> 32);
-            const int level = lc >> WALK_COUNT_BITS, count = lc & COUNT_MASK;
-            const int shift = 3 * (MAX_LEVEL - level);
-            const bool leaf = fc < 0;
+            const unsigned fcn = (unsigned)rec.fcn_next;
+            const int fc = (int)(fcn >> 4), next = (int)(rec.fcn_next >> 32), first = (int)rec.first_sc;
+            const unsigned sc = (unsigned)(rec.first_sc >> 32);
+            const int shift = (int)(sc >> WALK_COUNT_BITS), count = (int)(sc & (unsigned)COUNT_MASK);
+            const bool leaf = (fcn & 15u) == 0u;
             const bool inside = ((ki ^ kq) >> shift) == 0;
             bool accepted = false;
             if (FIXED ? (!inside && !leaf) : !inside) {
                 const double rx = __dsub_rn(xi, cx), ry = __dsub_rn(yi, cy), rz = __dsub_rn(zi, cz);
                 const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                accepted = s_cell2[level] < __dmul_rn(a.theta2, d2);
+                accepted = __longlong_as_double(rec.cell2) < __dmul_rn(a.theta2, d2);
             }
             if (accepted) {
                 have = true; from_node = true;

@@ -123,17 +123,16 @@ static int g_bh_exact = -1;
 
 static int default_ctx(grav_b200_ctx **out)
 {
-    if (!g_default) {
-        int dev = 0;
-        const char *e = getenv("GRAV_B200_DEVICE");
-        if (e) dev = atoi(e);
-        GB_TRY(grav_b200_ctx_create(&g_default, dev, 0, 1, nullptr));
-    }
+    if (!g_default) GB_TRY(grav_b200_ctx_create_auto(&g_default));   // GRAV_B200_DEVICE / GRAV_B200_DEVICES (team.cu)
     // the reference calls acceleration() from whatever thread owns the simulation
     // (a non-main Python thread, grav_sim/simulator.py:61-103): bind the device there
     GB_CUDA(cudaSetDevice(g_default->device));
-    g_default->bh_mode = grav_b200_get_bh_mode();
-    g_default->bh_exact = grav_b200_get_bh_exact();
+    const int mode = grav_b200_get_bh_mode(), exact = grav_b200_get_bh_exact();
+    if (g_default->bh_mode != mode || g_default->bh_exact != exact) {
+        if (g_default->team) GB_TRY(team_run(g_default, [=](grav_b200_ctx *r) { r->bh_mode = mode; r->bh_exact = exact; return GRAV_B200_OK; }));
+        g_default->bh_mode = mode;
+        g_default->bh_exact = exact;
+    }
     *out = g_default;
     return GRAV_B200_OK;
 }
@@ -247,6 +246,7 @@ int grav_b200_ctx_create(grav_b200_ctx **out, int device, int rank, int world_si
 void grav_b200_ctx_destroy(grav_b200_ctx *c)
 {
     if (!c) return;
+    if (team_active(c)) team_destroy(c);   // the workers destroy their own contexts on their own threads
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     whfast_state_free(c);
@@ -311,11 +311,20 @@ static int set_system_impl(grav_b200_ctx *c, int n, const double *x, const doubl
 
 int grav_b200_ctx_set_system(grav_b200_ctx *c, int n, const double *x, const double *v, const double *m, double G)
 {
+    GB_TEAM(c, grav_b200_ctx_set_system(r_, n, x, v, m, G));
     return set_system_impl(c, n, x, v, m, G, true);
+}
+
+// the one-shots' upload: velocities are never read
+static int set_system_no_velocities(grav_b200_ctx *c, int n, const double *x, const double *m, double G)
+{
+    GB_TEAM(c, set_system_no_velocities(r_, n, x, m, G));
+    return set_system_impl(c, n, x, nullptr, m, G, false);
 }
 
 int grav_b200_ctx_set_positions(grav_b200_ctx *c, const double *x)
 {
+    GB_TEAM(c, grav_b200_ctx_set_positions(r_, x));
     if (!c || !x || c->n < 1) { set_error("context has no system / NULL pointer"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     const size_t b3 = sizeof(double) * 3 * (size_t)c->n;
@@ -327,6 +336,7 @@ int grav_b200_ctx_set_positions(grav_b200_ctx *c, const double *x)
 
 int grav_b200_ctx_acceleration(grav_b200_ctx *c, int method, double eps, double theta, int max_leaf)
 {
+    GB_TEAM(c, grav_b200_ctx_acceleration(r_, method, eps, theta, max_leaf));
     if (!c || c->n < 1) { set_error("context has no system"); return GRAV_B200_EINVAL; }
     if (eps < 0.0) { set_error("Softening length is negative. Got: %.3g", eps); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
@@ -372,6 +382,14 @@ int grav_b200_ctx_acceleration(grav_b200_ctx *c, int method, double eps, double 
 static int download_aos3(grav_b200_ctx *c, double *d_src, double *h_dst, bool sharded)
 {
     GB_CUDA(cudaSetDevice(c->device));
+    if (c->team) {
+        // in-process team: the host array is shared by all members, so each writes the slice of its own targets (valid on
+        // every rank whatever produced it: owned shards of v and of the direct-sum a, the full Barnes-Hut a, own positions)
+        const size_t lo = 3 * (size_t)c->lo, cnt = 3 * (size_t)(c->hi - c->lo);
+        if (cnt) GB_CUDA(cudaMemcpyAsync(h_dst + lo, d_src + lo, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        return bh_check(c);
+    }
     if (sharded && c->world > 1) GB_TRY(comm_allgather_aos3(c, d_src));
     GB_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * 3 * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
     GB_CUDA(cudaStreamSynchronize(c->stream));
@@ -381,14 +399,16 @@ static int download_aos3(grav_b200_ctx *c, double *d_src, double *h_dst, bool sh
 int grav_b200_ctx_get_positions(grav_b200_ctx *c, double *x)
 {
     if (!c || !x || c->n < 1) { set_error("context has no system / NULL pointer"); return GRAV_B200_EINVAL; }
+    GB_TEAM(c, grav_b200_ctx_get_positions(r_, x));
     GB_CUDA(cudaSetDevice(c->device));
-    if (c->world > 1 && !c->posm_gathered) { GB_TRY(comm_allgather_posm(c)); c->posm_gathered = true; }
+    if (c->world > 1 && !c->posm_gathered && !c->team) { GB_TRY(comm_allgather_posm(c)); c->posm_gathered = true; }
     GB_TRY(unpack_positions(c, c->stage_a.as<double>()));
     return download_aos3(c, c->stage_a.as<double>(), x, false);
 }
 int grav_b200_ctx_get_velocities(grav_b200_ctx *c, double *v)
 {
     if (!c || !v || c->n < 1) { set_error("context has no system / NULL pointer"); return GRAV_B200_EINVAL; }
+    GB_TEAM(c, grav_b200_ctx_get_velocities(r_, v));
     GB_CUDA(cudaSetDevice(c->device));
     double *d_v;
     GB_TRY(synced_velocities(c, &d_v));
@@ -397,12 +417,14 @@ int grav_b200_ctx_get_velocities(grav_b200_ctx *c, double *v)
 int grav_b200_ctx_get_accelerations(grav_b200_ctx *c, double *a)
 {
     if (!c || !a || c->n < 1) { set_error("context has no system / NULL pointer"); return GRAV_B200_EINVAL; }
+    GB_TEAM(c, grav_b200_ctx_get_accelerations(r_, a));
     return download_aos3(c, c->acc.as<double>(), a, true);
 }
 
 int grav_b200_ctx_synchronize(grav_b200_ctx *c)
 {
     if (!c) { set_error("NULL context"); return GRAV_B200_EINVAL; }
+    GB_TEAM(c, grav_b200_ctx_synchronize(r_));
     GB_CUDA(cudaSetDevice(c->device));
     GB_CUDA(cudaStreamSynchronize(c->stream));
     return bh_check(c);
@@ -439,6 +461,7 @@ int grav_b200_ctx_event_elapsed_ms(grav_b200_ctx *c, int a, int b, float *ms)
 int grav_b200_ctx_flush_l2(grav_b200_ctx *c)
 {
     if (!c) { set_error("NULL context"); return GRAV_B200_EINVAL; }
+    GB_TEAM(c, grav_b200_ctx_flush_l2(r_));
     GB_CUDA(cudaSetDevice(c->device));
     const size_t bytes = (size_t)256 << 20;
     GB_TRY(c->l2_flush.reserve(bytes));
@@ -449,6 +472,7 @@ int grav_b200_ctx_flush_l2(grav_b200_ctx *c)
 int grav_b200_ctx_mark_positions_sharded(grav_b200_ctx *c)
 {
     if (!c) { set_error("NULL context"); return GRAV_B200_EINVAL; }
+    GB_TEAM(c, grav_b200_ctx_mark_positions_sharded(r_));
     if (c->world > 1) c->posm_gathered = false;
     return GRAV_B200_OK;
 }
@@ -473,14 +497,15 @@ static int one_shot(double *a, int n, const double *x, const double *m, double G
     std::lock_guard<std::mutex> lk(g_mu);
     grav_b200_ctx *c;
     GB_TRY(default_ctx(&c));
-    GB_TRY(set_system_impl(c, n, x, nullptr, m, G, false));
+    GB_TRY(set_system_no_velocities(c, n, x, m, G));
     for (;;) {
         GB_TRY(grav_b200_ctx_acceleration(c, method, eps, theta, leaf));
         const int rc = grav_b200_ctx_get_accelerations(c, a);
         // Barnes-Hut builds are queued without waiting for their sizes; a tree that outgrew its buffers is reported by
         // the download's synchronisation: rebuild with twice the room (the system is still resident)
         if (rc != GRAV_B200_ETREE || c->tree.slack >= 16) return rc;
-        c->tree.slack *= 2;
+        if (c->team) GB_TRY(team_run(c, [](grav_b200_ctx *r) { r->tree.slack *= 2; return GRAV_B200_OK; }));
+        else c->tree.slack *= 2;
     }
 }
 

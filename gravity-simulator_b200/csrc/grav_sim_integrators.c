@@ -236,7 +236,7 @@ int grav_b200_shim_leapfrog(ErrorStatus *out, System *system, IntegratorParam *i
     {
         TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
     }
-    TRY_RC(grav_b200_ctx_create(&ctx, resident_device(), 0, 1, NULL));
+    TRY_RC(grav_b200_ctx_create_auto(&ctx));   /* GRAV_B200_DEVICE, or a team of GRAV_B200_DEVICES GPUs driven from this thread */
     TRY_RC(grav_b200_ctx_set_system(ctx, system->num_particles, system->x, system->v, system->m, system->G));
     /* a(x0) and v_1/2 (:963-982) */
     TRY_RC(grav_b200_ctx_leapfrog_begin(ctx, method, acceleration_param->softening_length, acceleration_param->opening_angle,
@@ -343,7 +343,7 @@ static int fixed_step_resident(ErrorStatus *out, const int integrator, System *s
     {
         TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
     }
-    TRY_RC(grav_b200_ctx_create(&ctx, resident_device(), 0, 1, NULL));
+    TRY_RC(grav_b200_ctx_create_auto(&ctx));   /* GRAV_B200_DEVICE, or a team of GRAV_B200_DEVICES GPUs driven from this thread */
     TRY_RC(grav_b200_ctx_set_system(ctx, system->num_particles, system->x, system->v, system->m, system->G));
     TRY_RC(grav_b200_ctx_fixed_begin(ctx, integrator, method, acceleration_param->softening_length,
                                      acceleration_param->opening_angle, acceleration_param->max_num_particles_per_leaf));

@@ -251,6 +251,7 @@ extern "C" {
 
 int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *c, int method, double eps, double theta, int max_leaf, double dt)
 {
+    GB_TEAM(c, grav_b200_ctx_leapfrog_begin(r_, method, eps, theta, max_leaf, dt));
     if (!c || c->n < 1) { set_error("context has no system"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     const size_t b3 = sizeof(double) * 3 * (size_t)c->n;
@@ -269,6 +270,7 @@ int grav_b200_ctx_leapfrog_begin(grav_b200_ctx *c, int method, double eps, doubl
 
 int grav_b200_ctx_leapfrog_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
 {
+    GB_TEAM(c, grav_b200_ctx_leapfrog_steps(r_, dt, num_steps));
     if (!c || !c->lf_ready) { set_error("leapfrog_begin() has not been called"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     for (int64_t s = 0; s < num_steps; s++) {
@@ -289,6 +291,7 @@ int grav_b200_ctx_leapfrog_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
 
 int grav_b200_ctx_leapfrog_end(grav_b200_ctx *c)
 {
+    GB_TEAM(c, grav_b200_ctx_leapfrog_end(r_));
     if (!c || !c->lf_ready) { set_error("leapfrog_begin() has not been called"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     const size_t lo = 3 * (size_t)c->lo, hi = 3 * (size_t)c->hi;
@@ -305,6 +308,7 @@ int grav_b200_ctx_leapfrog_end(grav_b200_ctx *c)
 
 int grav_b200_ctx_fixed_begin(grav_b200_ctx *c, int integrator, int method, double eps, double theta, int max_leaf)
 {
+    GB_TEAM(c, grav_b200_ctx_fixed_begin(r_, integrator, method, eps, theta, max_leaf));
     if (!c || c->n < 1) { set_error("context has no system"); return GRAV_B200_EINVAL; }
     if (integrator != GRAV_B200_INTEGRATOR_EULER && integrator != GRAV_B200_INTEGRATOR_EULER_CROMER &&
         integrator != GRAV_B200_INTEGRATOR_RK4) {
@@ -330,6 +334,7 @@ int grav_b200_ctx_fixed_begin(grav_b200_ctx *c, int integrator, int method, doub
 
 int grav_b200_ctx_fixed_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
 {
+    GB_TEAM(c, grav_b200_ctx_fixed_steps(r_, dt, num_steps));
     if (!c || !c->fixed_integrator) { set_error("fixed_begin() has not been called"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     const int cnt = c->hi - c->lo;
@@ -375,6 +380,9 @@ int grav_b200_ctx_fixed_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
 
 int grav_b200_ctx_energy(grav_b200_ctx *c, double *energy)
 {
+    if (team_active(c)) {   // every member reduces to the same total; only the leader writes the caller's variable
+        return team_run(c, [=](grav_b200_ctx *r_) -> int { double other; return grav_b200_ctx_energy(r_, r_->rank == 0 ? energy : &other); });
+    }
     if (!c || !energy || c->n < 1) { set_error("context has no system / NULL pointer"); return GRAV_B200_EINVAL; }
     GB_CUDA(cudaSetDevice(c->device));
     if (c->world > 1 && !c->posm_gathered) { GB_TRY(comm_allgather_posm(c)); c->posm_gathered = true; }

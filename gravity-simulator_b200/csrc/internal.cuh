@@ -1,6 +1,7 @@
 // Internal declarations shared by the .cu files of libgrav_b200.so (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <functional>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -8,6 +9,7 @@
 #include "../../include/grav_b200.h"
 
 struct ncclComm;
+namespace gb { struct Team; }
 
 namespace gb {
 
@@ -87,13 +89,12 @@ struct WalkGeo {
     long long kq;      // key the inclusion test compares against (mode dependent)
 };
 struct WalkTopo {
-    int fc;            // id of the first child, -1 for a leaf
+    unsigned fcn;      // first child id << 4 | number of children; the low 4 bits are 0 for a leaf.  Also the walk's stack entry.
     int next;
     int first;         // sorted position of the node's first particle
-    int level_count;   // level << 26 | particles in the node (N <= 2^24 < 2^26)
+    unsigned shift_count;   // 3 (21 - level) << 26 | particles in the node (N <= 2^24 < 2^26): the key shift of the inclusion test
     double mass;
-    int nch;           // number of children (0 for a leaf)
-    int pad;
+    double cell2;      // (box_length / (2 << level))^2, the left-hand side of the opening test for this node's level
 };
 constexpr int WALK_COUNT_BITS = 26;
 static_assert(sizeof(WalkGeo) == 32 && sizeof(WalkTopo) == 32, "walk record layout");
@@ -145,6 +146,7 @@ struct grav_b200_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     ncclComm *comm = nullptr;
+    gb::Team *team = nullptr;   // member of an in-process device team (team.cu): public entries called on the leader fan out
 
     int n = 0;            // particles
     int n_pad = 0;        // n rounded up to SRC_PAD
@@ -172,6 +174,9 @@ struct grav_b200_ctx {
     gb::DevBuf rk_buf;            // RK4: x_0, v_0, xk1..3, vk1..3
 
     void *wh = nullptr;   // gb::WhfastState (whfast_resident.cu)
+    // per-device launch state of the radix sort (bh_sort.cu)
+    int sort_resident_ctas = -1;
+    bool sort_attr_scatter = false, sort_attr_onesweep = false;
 
     int bh_mode = 0;
     int bh_exact = 0;             // 1: bit-identical per-lane walk (GRAV_B200_BH_EXACT), 0: warp-cooperative walk, <= 1e-12
@@ -211,6 +216,15 @@ int comm_allgather_equal(grav_b200_ctx *c, double *d_base, size_t count_per_rank
 int leapfrog_kick(grav_b200_ctx *c, double dt_half_or_full);
 int leapfrog_drift(grav_b200_ctx *c, double dt);
 int synced_velocities(grav_b200_ctx *c, double **d_out);
+// team.cu
+bool team_active(const grav_b200_ctx *c);        // c leads (or belongs to) a team and this thread is not already inside a team call
+int team_run(grav_b200_ctx *c, const std::function<int(grav_b200_ctx *)> &f);
+void team_destroy(grav_b200_ctx *leader);
+// first statement of a public context entry: forward the call to every member of the team (r_ is the member's context)
+#define GB_TEAM(c, expr)                                                                              \
+    do {                                                                                              \
+        if (gb::team_active(c)) return gb::team_run((c), [=](grav_b200_ctx *r_) -> int { return (expr); }); \
+    } while (0)
 // timing helpers
 inline void stage_begin(grav_b200_ctx *c, int st) { cudaEventRecord(c->ev[2 * st], c->stream); }
 inline void stage_end(grav_b200_ctx *c, int st) { cudaEventRecord(c->ev[2 * st + 1], c->stream); c->ev_valid[st] = true; }

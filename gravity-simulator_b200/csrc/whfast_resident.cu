@@ -841,6 +841,7 @@ extern "C" {
 int grav_b200_ctx_whfast_begin(grav_b200_ctx *c, const int *particle_ids, int method, double eps, double dt,
                                int remove_invalid_particles)
 {
+    if (c && c->team) { set_error("the device-resident WHFast runs on one GPU: create its context with grav_b200_ctx_create(), not as a device team"); return GRAV_B200_EINVAL; }
     if (!c || c->n < 1) { set_error("context has no system"); return GRAV_B200_EINVAL; }
     if (c->world != 1) { set_error("device-resident WHFast runs on one GPU"); return GRAV_B200_EINVAL; }
     if (method != GRAV_B200_METHOD_PAIRWISE && method != GRAV_B200_METHOD_MASSLESS) {

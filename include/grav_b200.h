@@ -142,6 +142,20 @@ int grav_b200_ctx_create(grav_b200_ctx **out, int device, int rank, int world_si
 void grav_b200_ctx_destroy(grav_b200_ctx *ctx);
 int grav_b200_nccl_unique_id(void *out128);
 
+/* Device team: num_devices GPUs of this box driven from the ONE calling thread (the reference's callers,
+ * src/integrator.c:963,1021 and grav_sim/simulator.py:66-102, are single-process and single-threaded, so the
+ * one-process-per-GPU form above is out of their reach).  Returns the LEADER context (rank 0 on devices[0]; devices NULL =
+ * 0..num_devices-1); k-1 worker threads own the contexts of the other devices (ranks 1..k-1 of an in-process NCCL
+ * communicator).  Every grav_b200_ctx_* entry called on the leader runs on all members -- same sharding as with one
+ * process per GPU (direct sum by target range + all-gather of positions; Barnes-Hut replicated build + sharded walk) --
+ * and returns when all have returned; uploads read the caller's host arrays from every member, downloads write each
+ * member's own slice.  Not available for the resident WHFast (one GPU by design).  Destroy the leader to end the team.
+ * ctx_create_auto(): device GRAV_B200_DEVICE (default 0), or a team of GRAV_B200_DEVICES devices starting there -- what
+ * the host-pointer one-shots (the drop-in acceleration()) and the resident time loops of the drop-in build use. */
+int grav_b200_ctx_create_team(grav_b200_ctx **out, int num_devices, const int *devices);
+int grav_b200_ctx_create_auto(grav_b200_ctx **out);
+int grav_b200_ctx_team_size(const grav_b200_ctx *ctx);
+
 /* Upload the full system (host AoS, as in struct System, src/system.h:12-20).  v may be NULL.
  * With world_size>1 every rank passes the same arrays; rank r owns targets
  * [r*n/world, (r+1)*n/world) and keeps only their v / a up to date. */

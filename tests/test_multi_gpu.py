@@ -26,6 +26,16 @@ def test_two_gpu_parity(gb):
     assert "MULTI_GPU_CHECK_PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.mark.gpu
+def test_device_team_behind_the_drop_in(gb):
+    """GRAV_B200_DEVICES / grav_b200_ctx_create_team: k GPUs driven from one thread through the context API, through
+    acceleration() and through launch_simulation_python of the drop-in build (tests/team_check.py)."""
+    if gb.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "team_check.py"), "2"], capture_output=True, text=True, timeout=1500)
+    assert "TEAM_CHECK_PASSED" in r.stdout, r.stdout[-4000:] + r.stderr[-3000:]
+
+
 GLOO_WORKER = r'''
 import os, sys, json
 import numpy as np

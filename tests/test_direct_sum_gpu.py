@@ -104,7 +104,7 @@ def test_bench_size_sampled_targets_vs_reference_order(gb, oracle, ics, eps):
     ref = oracle.pairwise_targets(x, m, G, eps, tg)
     assert max_rel_err(a[tg], ref) <= TOL
     truth = oracle.pairwise_targets(x, m, G, eps, tg, long_double=True)
-    assert max_rel_err(a[tg], truth) <= max(max_rel_err(ref, truth), 1e-14)
+    assert max_rel_err(a[tg], truth) <= 2.0 * max_rel_err(ref, truth) + 1e-14
     # size-independent properties on the full vector
     assert np.isfinite(a).all()
     mom = (m[:, None] * a).sum(0)

@@ -263,24 +263,27 @@ def run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks):
                 parity = run["parity"] if parity is None or not run["parity"]["ok"] else parity
             # end to end through the reference-facing call with HOST buffers
             if not args.no_e2e:
-                a_host = np.empty((n, 3))
-                if world == 1:
-                    f = lambda: gb.acceleration(x, m, G, "barnes_hut", eps, theta, leaf)     # drop-in acceleration() symbol
-                    api = "acceleration() [method = barnes_hut] in libgrav_sim_b200.so"
-                else:
-                    def f():
-                        ctx.set_system(x, m, G)
-                        ctx.acceleration("barnes_hut", eps, theta, leaf)
-                        return ctx.accelerations(a_host)
-                    api = "grav_b200_ctx_set_system/_acceleration/_get_accelerations"
-                f()
+                e2e_s = 0.0
+                if rank == 0:      # the single-threaded drop-in call; with world > 1 it drives all GPUs (GRAV_B200_DEVICES, set above)
+                    a_host = np.empty((n, 3))
+                    pinned = []
+                    for arr in (x, m, a_host):
+                        try:
+                            gb.host_register(arr); pinned.append(arr)
+                        except Exception:
+                            pass
+                    f = lambda: gb.acceleration(x, m, G, "barnes_hut", eps, theta, leaf, out=a_host)
+                    f()
+                    t0 = time.perf_counter()
+                    f()
+                    e2e_s = time.perf_counter() - t0
+                    for arr in pinned:
+                        gb.host_unregister(arr)
                 barrier()
-                t0 = time.perf_counter()
-                out = f()
-                barrier()
-                e2e_s = max_over_ranks(time.perf_counter() - t0)
-                run["e2e"] = {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(x.nbytes + m.nbytes), "d2h_bytes_per_step": int(out.nbytes),
-                              "api": api}
+                e2e_s = max_over_ranks(e2e_s)
+                run["e2e"] = {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(x.nbytes + m.nbytes) * world, "d2h_bytes_per_step": int(3 * 8 * n),
+                              "api": "acceleration() [method = barnes_hut] in libgrav_sim_b200.so" + (f", GRAV_B200_DEVICES={world}" if world > 1 else ""),
+                              "host_memory": "pinned (cudaHostRegister on the caller's arrays)"}
             runs.append(run)
     # CPU baseline: the compiled reference, OpenMP walk on all host cores (its build phase is serial)
     cpu = None
@@ -415,25 +418,27 @@ def run_b200_arm(args):
                 gb.host_register(arr)
             except Exception:
                 pass
-        if world == 1:
-            def e2e_step():
-                return gb.acceleration(x, m, G, "pairwise", args.eps)   # the drop-in acceleration() symbol
-        else:
-            def e2e_step():
-                ctx.set_system(x, m, G)
-                ctx.acceleration("pairwise", args.eps)
-                return ctx.accelerations(a_host)
-        e2e_step()
+        # The call a user of the reference makes: the drop-in acceleration() symbol, host arrays in, host array out.  With
+        # N > 1 GPUs that single-threaded call drives all N devices itself (GRAV_B200_DEVICES=N: an in-process device team,
+        # include/grav_b200.h); rank 0 makes the call, the other ranks' processes wait at the barrier with their GPUs idle.
+        os.environ["GRAV_B200_DEVICES"] = str(world)      # read when the library creates its default context (first one-shot call)
+
+        def e2e_step():
+            return gb.acceleration(x, m, G, "pairwise", args.eps, out=a_host)
+        e2e_s = 0.0
+        if rank == 0:
+            e2e_step()
+            t0 = time.perf_counter()
+            ke = max(1, min(args.steps, 3))
+            for _ in range(ke):
+                out = e2e_step()
+            e2e_s = (time.perf_counter() - t0) / ke
         barrier()
-        t0 = time.perf_counter()
-        ke = max(1, min(args.steps, 3))
-        for _ in range(ke):
-            out = e2e_step()
-        barrier()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / ke)
-        e2e = {"value": inter / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + m.nbytes),
-               "d2h_bytes_per_step": int(out.nbytes), "ms_per_step": e2e_s * 1e3,
-               "api": "acceleration() in libgrav_sim_b200.so" if world == 1 else "grav_b200_ctx_set_system/_acceleration/_get_accelerations"}
+        e2e_s = max_over_ranks(e2e_s)
+        e2e = {"value": inter / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + m.nbytes) * world,
+               "d2h_bytes_per_step": int(a_host.nbytes), "ms_per_step": e2e_s * 1e3,
+               "api": "acceleration() in libgrav_sim_b200.so" + (f", GRAV_B200_DEVICES={world} (one calling thread drives {world} GPUs)" if world > 1 else ""),
+               "host_memory": "pinned (cudaHostRegister on the caller's arrays)"}
 
     # sampled parity of what was just timed, against the reference's arithmetic (checker only, outside every timed region)
     parity = None
@@ -473,6 +478,23 @@ def run_b200_arm(args):
                   "note": "9 x 1e5 interactions: a few launches of ~us each, bound by launch latency, not HBM"}
         except gb.GravB200Error as e:
             ml = {"unavailable": str(e)[:200]}
+
+    # energy diagnostic: the O(N^2) potential sum behind compute_energy(), resident state
+    en = None
+    if world == 1:
+        try:
+            ne = 1 << 17
+            xe, ve, me_, Ge = make_ic(args.ic, ne, seed=44)
+            ctx.set_system(xe, me_, Ge, ve)
+            ctx.energy()
+            ctx.event_record(6)
+            ctx.energy()
+            ctx.event_record(7)
+            e_ms = ctx.event_elapsed_ms(6, 7)
+            en = {"metric": "energy_eval_ms", "value": e_ms, "unit": "ms", "n": ne, "G_pairs_per_s": ne * (ne - 1.0) / (e_ms * 1e-3) / 1e9,
+                  "note": "13 FP64-pipe instructions per ordered pair (rsqrt seed + one correction), the direct sum's tile loop with a scalar reduction"}
+        except gb.GravB200Error as e:
+            en = {"unavailable": str(e)[:200]}
 
     # WHFast side measurement (config 3): device-resident steps vs the reference's whfast() on the host cores
     wh = None
@@ -526,7 +548,7 @@ def run_b200_arm(args):
                        # driver's parser, which keeps config whole, carries it into BENCH / SCALE
                        "barnes_hut": bh},
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "massless": ml, "whfast": wh, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "massless": ml, "whfast": wh, "energy": en, "gpu_launches": int(launches),
             "clocks": clocks, "allgather_ms": float(np.mean(gather_ms)) if world > 1 else 0.0,
         }
         print(json.dumps(line), flush=True)

@@ -249,12 +249,12 @@ def make_param(method, softening_length=0.0, opening_angle=1.0, max_num_particle
     return p
 
 
-def acceleration(x, m, G, method="pairwise", softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=-1):
-    """Host-buffer force evaluation through the drop-in `acceleration()` symbol. Returns a[N,3]."""
+def acceleration(x, m, G, method="pairwise", softening_length=0.0, opening_angle=1.0, max_num_particles_per_leaf=-1, out=None):
+    """Host-buffer force evaluation through the drop-in `acceleration()` symbol. Returns a[N,3] (written into `out` if given)."""
     _, shim = load()
     x = as_f64(x).reshape(-1, 3)
     m = as_f64(m).reshape(-1)
-    a = np.empty_like(x)
+    a = np.empty_like(x) if out is None else out
     sys_ = make_system(x, m, G)
     prm = make_param(method, softening_length, opening_angle, max_num_particles_per_leaf)
     check_status(shim.acceleration(_dp(a), C.byref(sys_), C.byref(prm)))

@@ -196,36 +196,56 @@ int synced_velocities(grav_b200_ctx *c, double **d_out)
 }
 
 // ---- energy -------------------------------------------------------------------------------------------
-// E = sum_i m_i |v_i|^2 / 2  -  G sum_{i<j} m_i m_j / |x_i - x_j|.  Each thread owns one particle i and sums
-// m_j / r_ij over all j != i (tiles through shared memory), so the pair sum is G/2 sum_i m_i pot_i.  Block
-// partial sums are written out and added in block order by one thread: deterministic.
+// E = sum_i m_i |v_i|^2 / 2  -  G sum_{i<j} m_i m_j / |x_i - x_j|  (compute_energy, src/utils.c:27-59; unsoftened).
+// Same tile machinery as the direct sum (direct_sum.cu): TI targets per thread in registers, sources streamed through a
+// shared-memory tile, and m_j / r_ij from the MUFU.RSQ64H seed y0 (|e| <~ 2^-20, e = 1 - r2 y0^2) with one correction,
+// r2^-1/2 = y0 (1 + e (1/2 + 3/8 e)) -- the dropped term 5/16 e^3 is < 2^-61 -- i.e. 13 FP64-pipe instructions per
+// ordered pair instead of the ~45 of sqrt + division.  Every thread sums m_j / r_ij over all j != i for its targets, so the
+// pair sum is G/2 sum_i m_i pot_i; block partial sums are written out and added in block order by one thread:
+// deterministic.  Coincident particles give a non-finite energy like the reference's 1/0.
+template <int TI>
 __global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__ posm, const double *__restrict__ v, int n, int n_pad,
                                                     int lo, int hi, double G, double *__restrict__ block_out)
 {
     __shared__ double4 tile[256];
     __shared__ double red[256];
-    const int i = lo + blockIdx.x * 256 + threadIdx.x;
-    const bool valid = i < hi;
-    double4 me = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (valid) me = posm[i];
-    double pot = 0.0;
+    double xi[TI], yi[TI], zi[TI], mi[TI], pot[TI];
+    int ii[TI];
+#pragma unroll
+    for (int t = 0; t < TI; t++) {
+        ii[t] = lo + (blockIdx.x * TI + t) * 256 + threadIdx.x;
+        const double4 me = (ii[t] < hi) ? posm[ii[t]] : make_double4(0.0, 0.0, 0.0, 0.0);
+        xi[t] = me.x; yi[t] = me.y; zi[t] = me.z; mi[t] = me.w;
+        pot[t] = 0.0;
+    }
     for (int j0 = 0; j0 < n_pad; j0 += 256) {
         __syncthreads();
         tile[threadIdx.x] = posm[j0 + threadIdx.x];
         __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < 256; j++) {
+        const int jcount = min(256, n - j0);          // padding sources are never visited
+#pragma unroll 2
+        for (int j = 0; j < jcount; j++) {
             const double4 q = tile[j];
-            const double dx = q.x - me.x, dy = q.y - me.y, dz = q.z - me.z;
-            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            // skip padding and the self term only: coincident particles give inf / NaN like the reference's 1/0
-            if ((j0 + j) < n && (j0 + j) != i) pot += q.w / sqrt(r2);
+#pragma unroll
+            for (int t = 0; t < TI; t++) {
+                const double dx = q.x - xi[t], dy = q.y - yi[t], dz = q.z - zi[t];
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                const double y = rsqrt_seed(r2);
+                const double e = fma(-r2, y * y, 1.0);
+                const double my = q.w * y;
+                double w = fma(my, e * fma(0.375, e, 0.5), my);     // m_j / r
+                if (j0 + j == ii[t]) w = 0.0;                         // the self term only
+                pot[t] += w;
+            }
         }
     }
     double e = 0.0;
-    if (valid) {
-        const double vx = v[3 * (size_t)i], vy = v[3 * (size_t)i + 1], vz = v[3 * (size_t)i + 2];
-        e = 0.5 * me.w * (vx * vx + vy * vy + vz * vz) - 0.5 * G * me.w * pot;
+#pragma unroll
+    for (int t = 0; t < TI; t++) {
+        if (ii[t] < hi) {
+            const double vx = v[3 * (size_t)ii[t]], vy = v[3 * (size_t)ii[t] + 1], vz = v[3 * (size_t)ii[t] + 2];
+            e += 0.5 * mi[t] * (vx * vx + vy * vy + vz * vz) - 0.5 * G * mi[t] * pot[t];
+        }
     }
     red[threadIdx.x] = e;
     __syncthreads();
@@ -389,11 +409,14 @@ int grav_b200_ctx_energy(grav_b200_ctx *c, double *energy)
     double *d_v;
     GB_TRY(synced_velocities(c, &d_v));
     const int cnt = c->hi - c->lo;
-    const int blocks = (cnt + 255) / 256;
+    // four targets per thread once that still leaves two CTAs per SM; one target per thread below (small systems need the CTAs)
+    const bool ti4 = (cnt + 1023) / 1024 >= 2 * c->sm_count;
+    const int blocks = ti4 ? (cnt + 1023) / 1024 : (cnt + 255) / 256;
     GB_TRY(c->misc.reserve(sizeof(double) * ((size_t)blocks + 2)));
     double *part = c->misc.as<double>();
     if (blocks > 0) {
-        energy_kernel<<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->G, part + 1);
+        if (ti4) energy_kernel<4><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->G, part + 1);
+        else energy_kernel<1><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->G, part + 1);
         GB_LAUNCH_CHECK();
         count_launch();
     }

@@ -263,6 +263,7 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     t.h_meta = nullptr;
     for (int i = 0; i < 2 * ST_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; i++) if (c->user_ev[i]) cudaEventDestroy(c->user_ev[i]);
+    mailbox_free(c);
     if (c->small_pinned) cudaFreeHost(c->small_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -515,7 +516,10 @@ int grav_b200_acceleration_pairwise(double *a, int n, const double *x, const dou
         std::lock_guard<std::mutex> lk(g_mu);
         grav_b200_ctx *c;
         GB_TRY(default_ctx(&c));
-        return direct_sum_small_host(c, a, n, x, m, G, eps);
+        // a resident kernel answers from a mailbox in pinned host memory (small_mailbox.cu); GRAV_B200_SMALL_MAILBOX=0 goes
+        // back to one launch + one synchronisation per call
+        static const bool use_mailbox = !(getenv("GRAV_B200_SMALL_MAILBOX") && atoi(getenv("GRAV_B200_SMALL_MAILBOX")) == 0);
+        return use_mailbox ? mailbox_pairwise(c, a, n, x, m, G, eps) : direct_sum_small_host(c, a, n, x, m, G, eps);
     }
     return one_shot(a, n, x, m, G, GRAV_B200_METHOD_PAIRWISE, eps, 0.0, 1);
 }

@@ -182,6 +182,7 @@ struct grav_b200_ctx {
     int bh_exact = 0;             // 1: bit-identical per-lane walk (GRAV_B200_BH_EXACT), 0: warp-cooperative walk, <= 1e-12
     cudaEvent_t user_ev[8] = {};
     gb::DevBuf l2_flush;
+    void *mailbox = nullptr;          // gb::MailboxState: resident small-system kernel (small_mailbox.cu)
     double *small_pinned = nullptr;   // mapped pinned host staging of the small-N one-shot path (in: 4n doubles, out: 3n)
     cudaEvent_t ev[2 * gb::ST_COUNT] = {};
     bool ev_valid[gb::ST_COUNT] = {};
@@ -192,6 +193,10 @@ namespace gb {
 int direct_sum_pairwise(grav_b200_ctx *c, double eps);
 int direct_sum_massless(grav_b200_ctx *c, double eps);
 int direct_sum_small_host(grav_b200_ctx *c, double *a, int n, const double *x, const double *m, double G, double eps);
+// small_mailbox.cu
+int mailbox_pairwise(grav_b200_ctx *c, double *a, int n, const double *x, const double *m, double G, double eps);
+int mailbox_stop(grav_b200_ctx *c);
+void mailbox_free(grav_b200_ctx *c);
 // pack.cu
 int pack_posm(grav_b200_ctx *c, const double *d_x_aos, const double *d_m);   // device AoS -> posm
 int pack_positions(grav_b200_ctx *c, const double *d_x_aos);

@@ -242,6 +242,18 @@ __global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__
     double e = 0.0;
 #pragma unroll
     for (int t = 0; t < TI; t++) {
+        if (ii[t] < hi && pot[t] != pot[t]) {
+            // r = 0 (another particle at the same point) turns the seed into inf and the correction into NaN; the reference
+            // divides by zero there (m / 0 = inf, or NaN for a massless partner): repeat this one target with the division
+            double p = 0.0;
+            for (int j = 0; j < n; j++) {
+                if (j == ii[t]) continue;
+                const double4 q = posm[j];
+                const double dx = q.x - xi[t], dy = q.y - yi[t], dz = q.z - zi[t];
+                p += q.w / sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+            }
+            pot[t] = p;
+        }
         if (ii[t] < hi) {
             const double vx = v[3 * (size_t)ii[t]], vy = v[3 * (size_t)ii[t] + 1], vz = v[3 * (size_t)ii[t] + 2];
             e += 0.5 * mi[t] * (vx * vx + vy * vy + vz * vz) - 0.5 * G * mi[t] * pot[t];

@@ -35,6 +35,7 @@ struct DSArgs {
     double *acc;              // AoS [3n], indexed by particle id
     double *partials;         // [grid][2][3][IB]
     int NB, NT;               // target blocks, source tiles
+    int gpt;                  // work granules per source tile (8 = 32 sources each, 1 = whole tiles): the unit of the even split
     int skip_special;         // fast kernel: leave the diagonal / padded tiles to direct_sum_special_kernel
 };
 
@@ -69,12 +70,13 @@ __device__ __forceinline__ void tile_interactions(const double4 *__restrict__ ti
                                                   const double *__restrict__ tile_altm, int j_base, int n_src,
                                                   const double (&xi)[TI], const double (&yi)[TI],
                                                   const double (&zi)[TI], const int (&ii)[TI],
-                                                  const bool (&alt)[TI], double eps2, Acc<TI> &a)
+                                                  const bool (&alt)[TI], double eps2, Acc<TI> &a, int ja = 0, int jb = DS_TJ)
 {
-    // checked loops stop at the last real source (the massless method has a handful of sources in a 256-wide tile)
-    const int jcount = CHECK ? min(DS_TJ, n_src - j_base) : DS_TJ;
+    // sources [ja, jb) of the tile (whole granules: multiples of 32); checked loops stop at the last real source (the
+    // massless method has a handful of sources in a 256-wide tile)
+    const int jcount = CHECK ? min(jb, n_src - j_base) : jb;
 #pragma unroll 2
-    for (int j = 0; j < jcount; j++) {
+    for (int j = ja; j < jcount; j++) {
         const double4 pj = tile[j];
         int jid = j_base + j;
         double altm = 0.0;
@@ -115,20 +117,24 @@ direct_sum_kernel(const DSArgs p)
     __shared__ double tile_altm[MASSLESS ? DS_TJ : 1];
 
     const int tid = threadIdx.x;
-    // unit range of this CTA (64-bit only for the product c*U; U itself fits in 32 bits for N <= 2^24)
-    const long long U = (long long)p.NB * p.NT;
+    // Granule range of this CTA.  The work of a target block is cut into granules of DS_TJ / gpt sources (32 when the
+    // problem is small enough to care: with whole tiles as the unit N = 16384 gave the CTAs 3 or 4 tiles each and the SMs
+    // 6 to 8, a 16 % tail).  64-bit only for the product c*U; the host keeps U below 2^31.
+    const int NG = p.NT * p.gpt;                        // granules per target block
+    const int gsz = DS_TJ / p.gpt;                      // sources per granule
+    const long long U = (long long)p.NB * NG;
     const int u0 = (int)unit_begin(blockIdx.x, U, gridDim.x);
     const int u1 = (int)unit_begin(blockIdx.x + 1, U, gridDim.x);
     if (u0 >= u1) return;
-    const int ib_first = u0 / p.NT;
+    const int ib_first = u0 / NG;
 
     int u = u0;
     while (u < u1) {
-        const int ib = u / p.NT;
-        const int jt0 = u - ib * p.NT;
-        const int seg_end = min(u1, (ib + 1) * p.NT);
-        const int jt1 = seg_end - ib * p.NT;
-        const bool full = (jt0 == 0 && jt1 == p.NT);
+        const int ib = u / NG;
+        const int ga = u - ib * NG;
+        const int seg_end = min(u1, (ib + 1) * NG);
+        const int gb = seg_end - ib * NG;
+        const bool full = (ga == 0 && gb == NG);
 
         // targets of this thread
         double xi[TI], yi[TI], zi[TI];
@@ -147,7 +153,9 @@ direct_sum_kernel(const DSArgs p)
         }
         const int blk_hi = min(blk_lo + IB, p.i_hi);   // exclusive
 
-        // stream the source tiles through shared memory (the second CTA of the SM computes meanwhile)
+        // stream the source tiles through shared memory (the second CTA of the SM computes meanwhile); the first and the
+        // last tile of the segment may be entered / left part-way
+        const int jt0 = ga / p.gpt, jt1 = (gb - 1) / p.gpt + 1;
         for (int jt = jt0; jt < jt1; jt++) {
             if (!CHECK && p.skip_special && tile_is_special(jt, p.n_src, blk_lo, blk_hi)) continue;   // block-uniform
             __syncthreads();
@@ -157,7 +165,8 @@ direct_sum_kernel(const DSArgs p)
                 tile_altm[tid] = p.src_altm[(size_t)jt * DS_TJ + tid];
             }
             __syncthreads();
-            tile_interactions<TI, CHECK, MASSLESS>(tile, tile_id, tile_altm, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
+            const int ja = max(ga - jt * p.gpt, 0) * gsz, jb = min(gb - jt * p.gpt, p.gpt) * gsz;
+            tile_interactions<TI, CHECK, MASSLESS>(tile, tile_id, tile_altm, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a, ja, jb);
         }
 
         if (full) {
@@ -236,9 +245,10 @@ __global__ void __launch_bounds__(DS_BLOCK) direct_sum_fixup_kernel(const DSArgs
     __shared__ int s_range[2];
     __shared__ signed char s_slot[DS_FIXUP_MAX_CONTRIB];     // 0 / 1: partial slot of contributor c_lo + k, -1: none
     const int ib = blockIdx.x;
-    const long long U = (long long)p.NB * p.NT;
+    const int NG = p.NT * p.gpt;
+    const long long U = (long long)p.NB * NG;
     if (threadIdx.x == 0) {
-        const long long ua = (long long)ib * p.NT, ub = ua + p.NT - 1;
+        const long long ua = (long long)ib * NG, ub = ua + NG - 1;
         // owner(u) = largest c with unit_begin(c) <= u
         auto owner = [&](long long u) {
             int lo = 0, hi = C - 1;
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(DS_BLOCK) direct_sum_fixup_kernel(const DSArgs
     for (int k = threadIdx.x; k <= c_hi - c_lo; k += DS_BLOCK) {
         const int c = c_lo + k;
         const long long b = unit_begin(c, U, C), e = unit_begin(c + 1, U, C);
-        s_slot[k] = (b >= e) ? -1 : (((int)(b / p.NT) == ib) ? 0 : 1);
+        s_slot[k] = (b >= e) ? -1 : (((int)(b / NG) == ib) ? 0 : 1);
     }
     __syncthreads();
     const int li = blockIdx.y * DS_BLOCK + threadIdx.x;
@@ -301,7 +311,9 @@ static int launch_direct_sum_t(grav_b200_ctx *c, DSArgs &a)
     const bool softened = !MASSLESS && a.eps2 >= 1e-60;
     const bool all_checked = !softened && (MASSLESS || a.NT <= checked_max_tiles);
     a.skip_special = softened ? 0 : 1;
-    const long long U = (long long)a.NB * a.NT;
+    // granules of 32 sources as the unit of the split while that keeps U in 31 bits (large problems do not need it)
+    a.gpt = ((long long)a.NB * a.NT * 8 < (1LL << 30)) ? 8 : 1;
+    const long long U = (long long)a.NB * a.NT * a.gpt;
     long long grid = (long long)c->sm_count * 2;
     if (grid > DS_FIXUP_MAX_CONTRIB) grid = DS_FIXUP_MAX_CONTRIB;   // the fix-up kernel's per-block contributor table
     if (grid > U) grid = U;
@@ -313,7 +325,7 @@ static int launch_direct_sum_t(grav_b200_ctx *c, DSArgs &a)
     count_launch();
     // a fix-up is needed iff some target block is split, i.e. unless every CTA boundary is a block boundary
     bool split = false;
-    for (long long k = 1; k < grid && !split; k++) split = (unit_begin(k, U, grid) % a.NT) != 0;
+    for (long long k = 1; k < grid && !split; k++) split = (unit_begin(k, U, grid) % ((long long)a.NT * a.gpt)) != 0;
     if (split) {
         direct_sum_fixup_kernel<TI><<<dim3(a.NB, TI), DS_BLOCK, 0, c->stream>>>(a, (int)grid);
         GB_LAUNCH_CHECK();

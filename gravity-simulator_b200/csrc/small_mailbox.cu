@@ -1,19 +1,31 @@
 // Small systems through the host-pointer API: a resident "mailbox" kernel instead of a launch per call.
 //
-// Config 1 of BASELINE.json (solar system, N = 9, IAS15) makes ~8 million acceleration() calls, each with 36 doubles of
-// input and 27 of output; the CPU reference needs ~2 us per call.  Round 1 answered every call with one kernel launch and
-// one stream synchronisation from mapped pinned staging: ~15 us, i.e. config 1 ran 28x slower than the reference through the
-// drop-in.  Launch + synchronise is a fixed cost no kernel change removes, so this path takes the launch out of the call:
+// Config 1 of BASELINE.json (solar system, N = 9, IAS15) makes ~20 million acceleration() calls per 1000 yr, each with 36
+// doubles of input and 27 of output; the CPU reference needs ~0.5 us per call.  Round 1 answered every call with one kernel
+// launch and one stream synchronisation from mapped pinned staging: 13.6 us per call in the real IAS15 loop.  Launch +
+// synchronise is a fixed cost no kernel change removes, so this path takes the launch out of the call:
 //
-//   * one CTA stays resident and polls a request word in mapped pinned HOST memory;
-//   * the host copies x, m into the mailbox, bumps the request word, and spins on the completion word;
-//   * the CTA reads the request (two PCIe round trips: the word, then the payload), evaluates all pairs from shared memory
-//     with the direct sum's arithmetic, writes a[] to the mailbox, fences and bumps the completion word.
+//   * one CTA stays resident and polls a request area in mapped pinned HOST memory;
+//   * the host copies n, G, eps^2, x, m into the request area and spins on the response area;
+//   * the CTA evaluates all pairs from shared memory with the direct sum's arithmetic and writes a[] to the response area.
+//
+// A call then costs PCIe round trips, so the protocol is built to need as few as possible -- ONE read round trip and one
+// posted write, no fences on either side:
+//   request   32-byte sectors of 3 doubles + a tag (the call number).  The host writes the tag of a sector last (x86 keeps
+//             the store order) and the device fetches host memory in 32-byte sectors, each served from one snapshot of its
+//             cache line, so a sector whose tag matches carries its payload.  Warp 0 polls the first 16 sectors with one
+//             coalesced 512-byte read: enough for n <= 11 (config 1); larger systems fetch the remaining sectors in a
+//             second round trip.
+//   response  16-byte items (value, tag), each written with one 16-byte store; the host accepts an item when its tag is the
+//             call number (it reads the tag first), so the device needs no fence between the data and a completion word.
+//
+// A first version used a request word, a payload read behind a system fence, a system fence after the results and a
+// completion word: five round trips, 13.6 us per call in the IAS15 loop -- no better than the launch it replaced.
 //
 // The kernel leaves by itself after MAILBOX_IDLE_US without a request (so nothing in the process can wait on it for longer:
-// cudaFree / cudaDeviceSynchronize of the application or of this library's other paths), when the host raises `quit` (any
-// larger call on the same context, context destruction), or when its lifetime budget runs out; the next small call starts it
-// again.  GRAV_B200_SMALL_MAILBOX=0 restores the launch-per-call path (direct_sum_small_host, direct_sum.cu).
+// cudaFree / cudaDeviceSynchronize of the application or of this library's other paths), when the host raises `quit`
+// (context destruction), or when its lifetime budget runs out; the next small call starts it again.
+// GRAV_B200_SMALL_MAILBOX=0 restores the launch-per-call path (direct_sum_small_host, direct_sum.cu).
 #include <time.h>
 
 #include "internal.cuh"
@@ -23,26 +35,27 @@ namespace gb {
 constexpr int MB_MAX = 256;                  // particles (one target per thread)
 constexpr unsigned long long MAILBOX_IDLE_US = 300;        // leave after this long without a request
 constexpr unsigned long long MAILBOX_LIFE_US = 2000000;    // and after this long in any case (bounds a forgotten kernel)
+constexpr int MB_HEAD = 3;                   // n, G, eps^2 precede x[3n], m[n] in the payload
+constexpr int MB_SECS = (MB_HEAD + 4 * MB_MAX + 2) / 3;   // 343 request sectors for n = 256
+constexpr int MB_POLL_SECS = 16;             // sectors fetched by every poll (one warp, 16 bytes per lane)
+
+struct ReqSec { double d[3]; unsigned long long tag; };
+struct RespItem { double v; unsigned long long tag; };
+static_assert(sizeof(ReqSec) == 32 && sizeof(RespItem) == 16, "mailbox layout");
 
 struct Mailbox {
-    // host -> device
-    volatile unsigned long long req;         // request number, written LAST by the host
-    int n;
-    int quit;
-    double G, eps2;
-    double x[3 * MB_MAX];
-    double m[MB_MAX];
-    // device -> host
-    double a[3 * MB_MAX];
-    volatile unsigned long long ack;         // number of the last completed request, written LAST by the device
-    volatile unsigned long long alive;       // set by the kernel when it starts polling, cleared when it leaves
+    ReqSec req[MB_SECS];                     // host -> device
+    RespItem resp[3 * MB_MAX];               // device -> host
+    volatile int quit;                       // host -> device
 };
 
-__device__ __forceinline__ unsigned long long ld_sys_u64(const volatile unsigned long long *p)
+__device__ __forceinline__ void ld_sys_v2(const void *p, unsigned long long &a, unsigned long long &b)
 {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_sys_v2(void *p, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
@@ -66,67 +79,73 @@ __device__ __forceinline__ void mb_interaction(const double4 pj, bool masked, do
     az = fma(s, dz, az);
 }
 
-__global__ void __launch_bounds__(MB_MAX) mailbox_kernel(Mailbox *mb)
+// chunk c (16 bytes) of the request area: the first half of sector c / 2 holds payload doubles 3 (c / 2) + 0, 1, the second
+// half holds double 3 (c / 2) + 2 and the tag
+__device__ __forceinline__ void stash_chunk(double *sP, int c, unsigned long long lo, unsigned long long hi)
 {
+    const int base = 3 * (c >> 1) + 2 * (c & 1);
+    sP[base] = __longlong_as_double((long long)lo);
+    if ((c & 1) == 0) sP[base + 1] = __longlong_as_double((long long)hi);
+}
+
+__global__ void __launch_bounds__(MB_MAX) mailbox_kernel(Mailbox *mb, unsigned long long last)
+{
+    __shared__ double sP[3 * MB_SECS];       // the payload, de-interleaved from the sectors
     __shared__ double4 src[MB_MAX];
     __shared__ unsigned long long s_req;
-    __shared__ int s_n;
-    __shared__ double s_G, s_eps2;
-    const int tid = threadIdx.x;
-    unsigned long long last = 0;
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned long long born = global_timer_ns();
-    if (tid == 0) {
-        last = ld_sys_u64(&mb->ack);
-        mb->alive = 1;
-        __threadfence_system();
-    }
     for (;;) {
-        if (tid == 0) {
+        if (tid < 32) {                      // warp 0 polls: one coalesced 512-byte read of the first 16 sectors per trip
             const unsigned long long idle0 = global_timer_ns();
-            unsigned long long r;
+            unsigned long long r = ~0ull;
             for (;;) {
-                r = ld_sys_u64(&mb->req);
-                if (r != last) break;
+                unsigned long long lo, hi;
+                ld_sys_v2((const char *)mb->req + 16 * lane, lo, hi);
+                const unsigned long long tag0 = __shfl_sync(0xffffffffu, hi, 1);
+                if (tag0 != last && tag0 != 0) {
+                    const int n = (int)__longlong_as_double((long long)__shfl_sync(0xffffffffu, lo, 0));
+                    const int nsec = (MB_HEAD + 4 * n + 2) / 3;
+                    const bool is_tag = (lane & 1) == 1 && (lane >> 1) < min(nsec, MB_POLL_SECS);
+                    if (__all_sync(0xffffffffu, !is_tag || hi == tag0)) {     // every polled sector of this request has arrived
+                        stash_chunk(sP, lane, lo, hi);
+                        r = tag0;
+                        break;
+                    }
+                }
                 const unsigned long long now = global_timer_ns();
-                if (*(volatile int *)&mb->quit || now - idle0 > MAILBOX_IDLE_US * 1000ull || now - born > MAILBOX_LIFE_US * 1000ull) { r = ~0ull; break; }
+                if (*(volatile int *)&mb->quit || now - idle0 > MAILBOX_IDLE_US * 1000ull || now - born > MAILBOX_LIFE_US * 1000ull) break;
             }
-            if (r != ~0ull) {
-                __threadfence_system();        // the payload was written before the request word
-                s_n = *(volatile int *)&mb->n;
-                s_G = *(volatile double *)&mb->G;
-                s_eps2 = *(volatile double *)&mb->eps2;
-            }
-            s_req = r;
+            if (lane == 0) s_req = r;
         }
         __syncthreads();
         const unsigned long long r = s_req;
         if (r == ~0ull) break;
-        const int n = s_n;
-        if (tid < n) {
-            const volatile double *hx = mb->x, *hm = mb->m;
-            src[tid] = make_double4(hx[3 * tid], hx[3 * tid + 1], hx[3 * tid + 2], hm[tid]);
+        const int n = (int)sP[0];
+        const int nsec = (MB_HEAD + 4 * n + 2) / 3;
+        for (int S = MB_POLL_SECS + tid; S < nsec; S += MB_MAX) {       // larger systems: the remaining sectors, one per thread
+            unsigned long long q[4];
+            do {
+                ld_sys_v2((const char *)&mb->req[S], q[0], q[1]);
+                ld_sys_v2((const char *)&mb->req[S] + 16, q[2], q[3]);
+            } while (q[3] != r);
+            stash_chunk(sP, 2 * S, q[0], q[1]);
+            stash_chunk(sP, 2 * S + 1, q[2], q[3]);
         }
+        __syncthreads();
+        const double G = sP[1], eps2 = sP[2];
+        if (tid < n) src[tid] = make_double4(sP[MB_HEAD + 3 * tid], sP[MB_HEAD + 3 * tid + 1], sP[MB_HEAD + 3 * tid + 2], sP[MB_HEAD + 3 * n + tid]);
         __syncthreads();
         if (tid < n) {
             const double4 me = src[tid];
             double ax = 0.0, ay = 0.0, az = 0.0;
-            for (int j = 0; j < n; j++) mb_interaction(src[j], j == tid, me.x, me.y, me.z, s_eps2, ax, ay, az);
-            volatile double *ha = mb->a;
-            ha[3 * tid + 0] = s_G * ax;
-            ha[3 * tid + 1] = s_G * ay;
-            ha[3 * tid + 2] = s_G * az;
-            __threadfence_system();            // results are in host memory before the completion word
+            for (int j = 0; j < n; j++) mb_interaction(src[j], j == tid, me.x, me.y, me.z, eps2, ax, ay, az);
+            st_sys_v2(&mb->resp[3 * tid + 0], (unsigned long long)__double_as_longlong(G * ax), r);
+            st_sys_v2(&mb->resp[3 * tid + 1], (unsigned long long)__double_as_longlong(G * ay), r);
+            st_sys_v2(&mb->resp[3 * tid + 2], (unsigned long long)__double_as_longlong(G * az), r);
         }
-        __syncthreads();
-        if (tid == 0) {
-            mb->ack = r;
-            __threadfence_system();
-            last = r;
-        }
-    }
-    if (tid == 0) {
-        mb->alive = 0;
-        __threadfence_system();
+        last = r;
+        __syncthreads();                     // sP / src are rewritten by the next request
     }
 }
 
@@ -144,11 +163,11 @@ static double now_s()
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-static int mailbox_start(grav_b200_ctx *c, MailboxState *s)
+static int mailbox_start(grav_b200_ctx *c, MailboxState *s, unsigned long long last_done)
 {
     s->mb->quit = 0;
     __sync_synchronize();
-    mailbox_kernel<<<1, MB_MAX, 0, s->stream>>>(s->mb);
+    mailbox_kernel<<<1, MB_MAX, 0, s->stream>>>(s->mb, last_done);
     GB_LAUNCH_CHECK();
     count_launch();
     s->launched = true;
@@ -197,25 +216,40 @@ int mailbox_pairwise(grav_b200_ctx *c, double *a, int n, const double *x, const 
         c->mailbox = s;
     }
     Mailbox *mb = s->mb;
-    memcpy(mb->x, x, sizeof(double) * 3 * (size_t)n);
-    memcpy(mb->m, m, sizeof(double) * (size_t)n);
-    mb->n = n;
-    mb->G = G;
-    mb->eps2 = eps * eps;
     const unsigned long long seq = ++s->seq;
-    __sync_synchronize();                  // payload before the request word (x86: a compiler barrier + store ordering)
-    mb->req = seq;
+    // payload stream: n, G, eps^2, x[3n], m[n]; three doubles per 32-byte sector, the sector's tag written last
+    const int total = MB_HEAD + 4 * n;
+    auto payload = [&](int k) -> double {
+        if (k == 0) return (double)n;
+        if (k == 1) return G;
+        if (k == 2) return eps * eps;
+        k -= MB_HEAD;
+        return k < 3 * n ? x[k] : m[k - 3 * n];
+    };
+    const int nsec = (total + 2) / 3;
+    for (int L = nsec - 1; L >= 0; L--) {          // sector 0 (the one the poll looks at first) last
+        ReqSec *ln = &mb->req[L];
+        for (int k = 0; k < 3; k++) ln->d[k] = (3 * L + k < total) ? payload(3 * L + k) : 0.0;
+        __asm__ __volatile__("" ::: "memory");     // x86 keeps the store order; the compiler must too
+        *(volatile unsigned long long *)&ln->tag = seq;
+    }
     __sync_synchronize();
-    if (!s->launched) GB_TRY(mailbox_start(c, s));
-    // wait for the completion word; now and then make sure the kernel is still there (it leaves when idle)
+    if (!s->launched) GB_TRY(mailbox_start(c, s, seq - 1));
+    // collect the response items; now and then make sure the kernel is still there (it leaves when idle)
     const double t0 = now_s();
     unsigned spins = 0;
-    while (mb->ack != seq) {
+    for (int k = 0; k < 3 * n;) {
+        const volatile RespItem *it = &mb->resp[k];
+        if (it->tag == seq) {
+            __asm__ __volatile__("" ::: "memory");
+            a[k] = it->v;
+            k++;
+            continue;
+        }
         if ((++spins & 0x3ff) == 0) {
             if (cudaStreamQuery(s->stream) == cudaSuccess) {      // the kernel left (idle / lifetime) without seeing this request
                 s->launched = false;
-                if (mb->ack == seq) break;
-                GB_TRY(mailbox_start(c, s));
+                GB_TRY(mailbox_start(c, s, seq - 1));
             } else {
                 cudaGetLastError();                                 // cudaErrorNotReady is the normal answer
             }
@@ -227,8 +261,6 @@ int mailbox_pairwise(grav_b200_ctx *c, double *a, int n, const double *x, const 
         }
         __builtin_ia32_pause();
     }
-    __sync_synchronize();
-    memcpy(a, mb->a, sizeof(double) * 3 * (size_t)n);
     return GRAV_B200_OK;
 }
 

@@ -15,7 +15,12 @@ ins = [re.sub(r"/\* 0x[0-9a-f]+ \*/", "", l).rstrip() for l in out.splitlines() 
 # the loop: from the first LDS.128 after the second BAR.SYNC to the backward BRA.U
 bars = [i for i, l in enumerate(ins) if "BAR.SYNC" in l]
 start = next(i for i in range(bars[1], len(ins)) if "LDS.128" in ins[i])
-end = next(i for i in range(start, len(ins)) if "BRA.U" in ins[i])
+def is_back_branch(i):
+    m = re.search(r"/\*([0-9a-f]{4})\*/.*\bBRA(?:\.U)?\b.*0x([0-9a-f]+)", ins[i])
+    return bool(m) and int(m.group(2), 16) <= int(m.group(1), 16) and "MUFU" in " ".join(ins[start:i])
+end = next(i for i in range(start, len(ins)) if is_back_branch(i))
+start = max(k for k in range(start, end) if re.search(r"/\*([0-9a-f]{4})\*/", ins[k]) and
+            int(re.search(r"/\*([0-9a-f]{4})\*/", ins[k]).group(1), 16) <= int(re.search(r"0x([0-9a-f]+)", ins[end].split("BRA")[1]).group(1), 16))
 loop = ins[start:end + 1]
 print(f"# {fun}\n# inner loop: {len(loop)} instructions for 2 sources x 4 targets = 8 interactions\n")
 for l in loop:

@@ -107,7 +107,9 @@ __device__ __forceinline__ bool tile_is_special(int jt, int n_src, int blk_lo, i
 // Main kernel.  CHECK=false: the fast loop only; special tiles are SKIPPED (direct_sum_special_kernel adds
 // them afterwards), which keeps this kernel's code identical to the tuned loop (one inner-loop variant, no
 // extra live registers).  CHECK=true: every tile goes through the checked loop (small problems, massless).
-template <int TI, bool CHECK, bool MASSLESS>
+//   GRAN: the even split cuts at 32-source granules (small problems) instead of whole tiles.  The variable inner-loop bounds
+//   cost the tuned loop 6 % (128 registers, no slack for ptxas), which pays only while a CTA gets fewer than ~16 tiles.
+template <int TI, bool CHECK, bool MASSLESS, bool GRAN>
 __global__ void __launch_bounds__(DS_BLOCK, 2)   // tuned on B200: TI=4, 2 CTAs/SM, unroll 2 (scratch/ds_tune.cu)
 direct_sum_kernel(const DSArgs p)
 {
@@ -120,8 +122,9 @@ direct_sum_kernel(const DSArgs p)
     // Granule range of this CTA.  The work of a target block is cut into granules of DS_TJ / gpt sources (32 when the
     // problem is small enough to care: with whole tiles as the unit N = 16384 gave the CTAs 3 or 4 tiles each and the SMs
     // 6 to 8, a 16 % tail).  64-bit only for the product c*U; the host keeps U below 2^31.
-    const int NG = p.NT * p.gpt;                        // granules per target block
-    const int gsz = DS_TJ / p.gpt;                      // sources per granule
+    const int gpt = GRAN ? p.gpt : 1;
+    const int NG = p.NT * gpt;                          // granules per target block
+    const int gsz = DS_TJ / gpt;                        // sources per granule
     const long long U = (long long)p.NB * NG;
     const int u0 = (int)unit_begin(blockIdx.x, U, gridDim.x);
     const int u1 = (int)unit_begin(blockIdx.x + 1, U, gridDim.x);
@@ -155,7 +158,7 @@ direct_sum_kernel(const DSArgs p)
 
         // stream the source tiles through shared memory (the second CTA of the SM computes meanwhile); the first and the
         // last tile of the segment may be entered / left part-way
-        const int jt0 = ga / p.gpt, jt1 = (gb - 1) / p.gpt + 1;
+        const int jt0 = ga / gpt, jt1 = (gb - 1) / gpt + 1;
         for (int jt = jt0; jt < jt1; jt++) {
             if (!CHECK && p.skip_special && tile_is_special(jt, p.n_src, blk_lo, blk_hi)) continue;   // block-uniform
             __syncthreads();
@@ -165,8 +168,12 @@ direct_sum_kernel(const DSArgs p)
                 tile_altm[tid] = p.src_altm[(size_t)jt * DS_TJ + tid];
             }
             __syncthreads();
-            const int ja = max(ga - jt * p.gpt, 0) * gsz, jb = min(gb - jt * p.gpt, p.gpt) * gsz;
-            tile_interactions<TI, CHECK, MASSLESS>(tile, tile_id, tile_altm, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a, ja, jb);
+            if (GRAN) {
+                const int ja = max(ga - jt * gpt, 0) * gsz, jb = min(gb - jt * gpt, gpt) * gsz;
+                tile_interactions<TI, CHECK, MASSLESS>(tile, tile_id, tile_altm, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a, ja, jb);
+            } else {
+                tile_interactions<TI, CHECK, MASSLESS>(tile, tile_id, tile_altm, jt * DS_TJ, p.n_src, xi, yi, zi, ii, alt, p.eps2, a);
+            }
         }
 
         if (full) {
@@ -311,16 +318,21 @@ static int launch_direct_sum_t(grav_b200_ctx *c, DSArgs &a)
     const bool softened = !MASSLESS && a.eps2 >= 1e-60;
     const bool all_checked = !softened && (MASSLESS || a.NT <= checked_max_tiles);
     a.skip_special = softened ? 0 : 1;
-    // granules of 32 sources as the unit of the split while that keeps U in 31 bits (large problems do not need it)
-    a.gpt = ((long long)a.NB * a.NT * 8 < (1LL << 30)) ? 8 : 1;
-    const long long U = (long long)a.NB * a.NT * a.gpt;
+    // granules of 32 sources as the unit of the split while a CTA gets fewer than 16 tiles (N <~ 40000 on one GPU)
     long long grid = (long long)c->sm_count * 2;
+    a.gpt = ((long long)a.NB * a.NT < 16 * grid) ? 8 : 1;
+    const long long U = (long long)a.NB * a.NT * a.gpt;
     if (grid > DS_FIXUP_MAX_CONTRIB) grid = DS_FIXUP_MAX_CONTRIB;   // the fix-up kernel's per-block contributor table
     if (grid > U) grid = U;
     GB_TRY(c->partials.reserve((size_t)grid * 2 * 3 * IB * sizeof(double)));
     a.partials = c->partials.as<double>();
-    if (all_checked) direct_sum_kernel<TI, true, MASSLESS><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
-    else direct_sum_kernel<TI, false, false><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+    if (all_checked) {
+        if (a.gpt > 1) direct_sum_kernel<TI, true, MASSLESS, true><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+        else direct_sum_kernel<TI, true, MASSLESS, false><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+    } else {
+        if (a.gpt > 1) direct_sum_kernel<TI, false, false, true><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+        else direct_sum_kernel<TI, false, false, false><<<(unsigned)grid, DS_BLOCK, 0, c->stream>>>(a);
+    }
     GB_LAUNCH_CHECK();
     count_launch();
     // a fix-up is needed iff some target block is split, i.e. unless every CTA boundary is a block boundary

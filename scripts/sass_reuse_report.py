@@ -1,4 +1,4 @@
-"""Inner loop of direct_sum_kernel<4,false,false> as ptxas emitted it: FP64 instruction mix and how many of the accumulate
+"""Inner loop of direct_sum_kernel<4,false,false,false> as ptxas emitted it: FP64 instruction mix and how many of the accumulate
 DFMAs (three distinct register operands = 3 FP64-pipe cycles) can take an operand from the reuse cache,
 i.e. directly follow an FP64 instruction that flagged the same register `.reuse`.
     python scripts/sass_reuse_report.py > profiles/r2_direct_sum_inner_loop_sass.txt"""
@@ -9,7 +9,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 obj = ROOT / "gravity-simulator_b200" / "build" / "direct_sum.o"
-fun = "_ZN2gb17direct_sum_kernelILi4ELb0ELb0EEEvNS_6DSArgsE"
+fun = "_ZN2gb17direct_sum_kernelILi4ELb0ELb0ELb0EEEvNS_6DSArgsE"
 out = subprocess.run(["cuobjdump", "-sass", "-fun", fun, str(obj)], capture_output=True, text=True, check=True).stdout
 ins = [re.sub(r"/\* 0x[0-9a-f]+ \*/", "", l).rstrip() for l in out.splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", l)]
 # the loop: from the first LDS.128 after the second BAR.SYNC to the backward BRA.U

@@ -495,6 +495,8 @@ typedef struct WalkCtx {
     double xi[3], acc[3];
     /* statistics of the current target (oracle_bh_walk_stats) */
     long long visits, accepts, opened, leaf_particles;
+    int *opened_ids;        /* optional: ids of the opened nodes, in walk order */
+    long long opened_cap;
 } WalkCtx;
 
 static void walk_children(WalkCtx *w, int node, int level)
@@ -533,6 +535,7 @@ static void walk_children(WalkCtx *w, int node, int level)
                 w->acc[0] -= f * rx; w->acc[1] -= f * ry; w->acc[2] -= f * rz;
             }
         } else {
+            if (w->opened_ids && w->opened < w->opened_cap) w->opened_ids[w->opened] = c;
             w->opened++;
             walk_children(w, c, level + 1);
         }
@@ -541,10 +544,24 @@ static void walk_children(WalkCtx *w, int node, int level)
 
 static void walk_one(WalkCtx *w, const OracleTree *t, const double *x, int p, int fixed_mode);
 
+/* ids of the nodes the walk of the target at sorted position p opens (design studies of shared traversals); returns the count */
+long long oracle_bh_walk_opened(const OracleTree *t, const double *x, const double *m, double theta, int fixed_mode, int p,
+                                int *ids, long long cap)
+{
+    WalkCtx w;
+    w.t = t; w.x = x; w.m = m; w.G = 1.0; w.eps2 = 0.0; w.theta2 = theta * theta;
+    w.box_length = t->box_width * 2.0;
+    w.fixed = fixed_mode;
+    w.opened_ids = ids; w.opened_cap = cap;
+    walk_one(&w, t, x, p, fixed_mode);
+    return w.opened;
+}
+
 void oracle_bh_walk(double *a, const OracleTree *t, const double *x, const double *m, double G, double eps,
                     double theta, int fixed_mode)
 {
     WalkCtx w;
+    w.opened_ids = NULL; w.opened_cap = 0;
     w.t = t; w.x = x; w.m = m; w.G = G; w.eps2 = eps * eps; w.theta2 = theta * theta;
     w.box_length = t->box_width * 2.0;
     w.fixed = fixed_mode;
@@ -579,6 +596,7 @@ void oracle_bh_walk_targets(double *a, long long *stats, const OracleTree *t, co
         w.t = t; w.x = x; w.m = m; w.G = G; w.eps2 = eps * eps; w.theta2 = theta * theta;
         w.box_length = t->box_width * 2.0;
         w.fixed = fixed_mode;
+        w.opened_ids = NULL; w.opened_cap = 0;
         walk_one(&w, t, x, positions[k], fixed_mode);
         a[3 * k] = w.acc[0]; a[3 * k + 1] = w.acc[1]; a[3 * k + 2] = w.acc[2];
         if (stats) {

@@ -212,7 +212,7 @@ def _ncu_bh_traffic():
         return None
 
 
-def run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks):
+def run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks, idle_until_rank0):
     from oracle.bind import Oracle, Reference
     theta, leaf, eps = 0.5, 1, args.eps
     sizes = sorted({args.bh_n, min(args.bh_n, 1 << 20)}, reverse=True)
@@ -263,8 +263,7 @@ def run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks):
                 parity = run["parity"] if parity is None or not run["parity"]["ok"] else parity
             # end to end through the reference-facing call with HOST buffers
             if not args.no_e2e:
-                e2e_s = 0.0
-                if rank == 0:      # the single-threaded drop-in call; with world > 1 it drives all GPUs (GRAV_B200_DEVICES, set above)
+                def e2e_run():     # the single-threaded drop-in call; with world > 1 it drives all GPUs (GRAV_B200_DEVICES, set above)
                     a_host = np.empty((n, 3))
                     pinned = []
                     for arr in (x, m, a_host):
@@ -276,9 +275,13 @@ def run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks):
                     f()
                     t0 = time.perf_counter()
                     f()
-                    e2e_s = time.perf_counter() - t0
+                    dt = time.perf_counter() - t0
                     for arr in pinned:
                         gb.host_unregister(arr)
+                    return dt
+                ctx.synchronize()
+                barrier()
+                e2e_s = idle_until_rank0(e2e_run) or 0.0
                 barrier()
                 e2e_s = max_over_ranks(e2e_s)
                 run["e2e"] = {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(x.nbytes + m.nbytes) * world, "d2h_bytes_per_step": int(3 * 8 * n),
@@ -337,6 +340,27 @@ def run_b200_arm(args):
     def barrier():
         if dist is not None:
             dist.barrier()
+
+    _tags = [0]
+
+    def idle_until_rank0(work):
+        """rank 0 runs work(); the other ranks wait ON THE CPU (TCP store), leaving their GPUs idle.  A dist.barrier() would
+        park an NCCL kernel on every waiting GPU, and a GPU shared by two processes is time-sliced: the device team that
+        rank 0's single-threaded acceleration() call drives would get half of each of the other GPUs."""
+        if dist is None:
+            return work()
+        _tags[0] += 1
+        key = f"rank0_done_{_tags[0]}"
+        store = dist.distributed_c10d._get_default_store()
+        out = None
+        if rank == 0:
+            try:
+                out = work()
+            finally:
+                store.set(key, "1")
+        else:
+            store.wait([key])
+        return out
 
     def max_over_ranks(val):
         if dist is None:
@@ -425,14 +449,16 @@ def run_b200_arm(args):
 
         def e2e_step():
             return gb.acceleration(x, m, G, "pairwise", args.eps, out=a_host)
-        e2e_s = 0.0
-        if rank == 0:
+        def e2e_run():
             e2e_step()
             t0 = time.perf_counter()
             ke = max(1, min(args.steps, 3))
             for _ in range(ke):
-                out = e2e_step()
-            e2e_s = (time.perf_counter() - t0) / ke
+                e2e_step()
+            return (time.perf_counter() - t0) / ke
+        ctx.synchronize()
+        barrier()
+        e2e_s = idle_until_rank0(e2e_run) or 0.0
         barrier()
         e2e_s = max_over_ranks(e2e_s)
         e2e = {"value": inter / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + m.nbytes) * world,
@@ -451,7 +477,7 @@ def run_b200_arm(args):
     bh = None
     if args.bh_n > 0:
         try:
-            bh = run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks)
+            bh = run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks, idle_until_rank0)
         except gb.GravB200Error as e:
             bh = {"unavailable": str(e)[:200]}
 

@@ -292,6 +292,11 @@ def run_barnes_hut(args, gb, ctx, rank, world, barrier, max_over_ranks, idle_unt
     cpu = None
     if rank == 0 and args.bh_cpu_n > 0:
         impl, kname = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
+        try:   # torchrun exports OMP_NUM_THREADS=1; the baseline is the reference's OpenMP walk on ALL host cores
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count())
+        except OSError:
+            pass
         cpu = {"unit": "s", "cores": os.cpu_count() if kname == "reference" else 1, "kind": kname, "n": args.bh_cpu_n, "runs": []}
         for ic in ("plummer", "uniform"):
             x, v, m, G = make_ic(ic, args.bh_cpu_n, seed=43)

@@ -60,7 +60,7 @@ __global__ void tree_init_kernel(ExpRec *rec, TreeMeta *meta, int n)
         meta->lvl_off[threadIdx.x] = 0;
     }
     if (threadIdx.x == 0) {
-        meta->num_expanded = 0; meta->num_nodes = 0; meta->levels = 0; meta->overflow = 0;
+        meta->num_expanded = 0; meta->num_nodes = 0; meta->levels = 0; meta->overflow = 0; meta->coop_barrier = 0;
         ExpRec r;
         for (int k = 0; k < 9; k++) r.b[k] = 0;
         r.b[0] = 0; r.b[1] = n;
@@ -75,9 +75,10 @@ __global__ void tree_init_kernel(ExpRec *rec, TreeMeta *meta, int n)
 // more than max_leaf particles get a record in the next level.  Record slots: the CTA adds up what its 32 nodes need and
 // takes them with ONE atomicAdd on the next level's counter (an atomic per node would serialise ~10^6 operations on one
 // address at N = 2^24).
-__global__ void __launch_bounds__(EXPAND_THREADS) expand_kernel(ExpRec *__restrict__ rec, TreeMeta *__restrict__ meta, int l,
-                                                               const long long *__restrict__ K, int max_leaf,
-                                                               int *__restrict__ W, int ne_cap)
+// (bid, nblocks): the calling grid; rec / meta / W are also written by other phases of the single-launch build below, so they
+// are plain pointers here (no read-only loads).
+__device__ __forceinline__ void expand_level(ExpRec *rec, TreeMeta *meta, int l, const long long *__restrict__ K, int max_leaf,
+                                             int *W, int ne_cap, int bid, int nblocks)
 {
     __shared__ int s_warp_tot[EXPAND_THREADS / 32];
     __shared__ int s_base;
@@ -85,12 +86,12 @@ __global__ void __launch_bounds__(EXPAND_THREADS) expand_kernel(ExpRec *__restri
     int count = meta->lvl_cnt[l];
     if (begin + count > ne_cap) count = max(0, ne_cap - begin);   // overflow (flagged below): those records were never written
     const int next_begin = begin + count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) meta->lvl_off[l + 1] = next_begin;
+    if (bid == 0 && threadIdx.x == 0) meta->lvl_off[l + 1] = next_begin;
     const int o = threadIdx.x & 7, oct = threadIdx.x >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g0 = lane & ~7;
     const unsigned gmask = 0xffu << g0;
     const int cl = l + 1, shift = 3 * (MAX_LEVEL - cl);            // level of the children
-    for (int t0 = blockIdx.x * (EXPAND_THREADS / 8); t0 < count; t0 += gridDim.x * (EXPAND_THREADS / 8)) {   // CTA-uniform
+    for (int t0 = bid * (EXPAND_THREADS / 8); t0 < count; t0 += nblocks * (EXPAND_THREADS / 8)) {   // CTA-uniform
         const int t = t0 + oct;
         const bool valid = t < count;
         ExpRec *r = rec + begin + (valid ? t : 0);
@@ -157,10 +158,15 @@ __global__ void __launch_bounds__(EXPAND_THREADS) expand_kernel(ExpRec *__restri
     }
 }
 
-// After the discovery and the scan of W: totals, overflow flags, box width and the walk's cell sizes.
-__global__ void tree_meta_kernel(TreeMeta *meta, const int *__restrict__ P, int n, const double *__restrict__ box, int ne_cap, int m_cap)
+__global__ void __launch_bounds__(EXPAND_THREADS) expand_kernel(ExpRec *rec, TreeMeta *meta, int l, const long long *__restrict__ K,
+                                                               int max_leaf, int *W, int ne_cap)
 {
-    if (threadIdx.x != 0) return;
+    expand_level(rec, meta, l, K, max_leaf, W, ne_cap, blockIdx.x, gridDim.x);
+}
+
+// After the discovery and the scan of W: totals, overflow flags, box width and the walk's cell sizes.
+__device__ __forceinline__ void tree_meta_body(TreeMeta *meta, const int *P, int n, const double *__restrict__ box, int ne_cap, int m_cap)
+{
     int ne = 0, levels = 0;
     for (int l = 0; l <= MAX_LEVEL; l++) {
         const int cnt = meta->lvl_cnt[l];
@@ -182,6 +188,11 @@ __global__ void tree_meta_kernel(TreeMeta *meta, const int *__restrict__ P, int 
     }
 }
 
+__global__ void tree_meta_kernel(TreeMeta *meta, const int *P, int n, const double *__restrict__ box, int ne_cap, int m_cap)
+{
+    if (threadIdx.x == 0) tree_meta_body(meta, P, n, box, ne_cap, m_cap);
+}
+
 // Numbering, topology and ropes in one pass over the expanded records, eight lanes per record (one per child).
 //   first_child(u) = 1 + P[s_u] + same_start(u);  id(u) = first_child(parent) + rank  -- both pure functions of the
 //   records' positions, so nothing here waits for another record's result.
@@ -192,14 +203,13 @@ __global__ void tree_meta_kernel(TreeMeta *meta, const int *__restrict__ P, int 
 //   climbing while the node is itself a last child (1.3 steps on average); the root's rope ends the walk.
 //   Inclusion key: reference mode reproduces the walk's fetch keys[sorted_indices[first_particle]] -- the SORTED key
 //   array indexed by an ORIGINAL particle id (src/acceleration_barnes_hut.c:143-147); fixed mode uses the node's own key.
-__global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *__restrict__ rec, const TreeMeta *__restrict__ meta, int n, int max_leaf,
-                                                        const int *__restrict__ P, const long long *__restrict__ K,
-                                                        const int *__restrict__ perm, int fixed_mode,
-                                                        WalkGeo *__restrict__ geo, WalkTopo *__restrict__ topo)
+__device__ __forceinline__ void fill_nodes_body(ExpRec *rec, const TreeMeta *meta, int n, int max_leaf, const int *P,
+                                                const long long *__restrict__ K, const int *__restrict__ perm, int fixed_mode,
+                                                WalkGeo *geo, WalkTopo *topo, int bid, int nblocks)
 {
     if (meta->overflow) return;                      // ids would run past the planes; the host reports the flag
     const int ne = meta->num_expanded;
-    for (int gt = blockIdx.x * blockDim.x + threadIdx.x; (gt >> 3) < ne; gt += gridDim.x * blockDim.x) {
+    for (int gt = bid * blockDim.x + threadIdx.x; (gt >> 3) < ne; gt += nblocks * blockDim.x) {
         const int u = gt >> 3, k = gt & 7;
         const ExpRec r = rec[u];
         const int fcu = 1 + P[r.b[0]] + r.same_start;
@@ -247,22 +257,28 @@ __global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *__restrict__ re
     }
 }
 
+__global__ void __launch_bounds__(256) fill_nodes_kernel(ExpRec *rec, const TreeMeta *meta, int n, int max_leaf, const int *P,
+                                                        const long long *__restrict__ K, const int *__restrict__ perm, int fixed_mode,
+                                                        WalkGeo *geo, WalkTopo *topo)
+{
+    fill_nodes_body(rec, meta, n, max_leaf, P, K, perm, fixed_mode, geo, topo, blockIdx.x, gridDim.x);
+}
+
 // One level of the moments.  Eight lanes per expanded node, one per child: the loads of the children's contributions (a
 // leaf's particle from the Morton-sorted copy, an expanded child's finished sums) go out together; then every lane of
 // the octet adds the items up in the reference's order (children in id order, the particles of a leaf one at a time), so
 // the sums are bit-identical to the serial loop.  Leaves with several particles (max_leaf > 1, or duplicates at level
 // 21) are read in the ordered phase by all eight lanes (same address: one transaction).
-__global__ void __launch_bounds__(128) moments_kernel(const ExpRec *__restrict__ rec, const TreeMeta *__restrict__ meta, int l,
-                                                     int max_leaf, const double4 *__restrict__ psorted,
-                                                     WalkGeo *__restrict__ geo, WalkTopo *__restrict__ topo,
-                                                     double *__restrict__ mtd)
+__device__ __forceinline__ void moments_level(const ExpRec *rec, const TreeMeta *meta, int l, int max_leaf,
+                                              const double4 *__restrict__ psorted, WalkGeo *geo, WalkTopo *topo, double *mtd,
+                                              int bid, int nblocks)
 {
     if (meta->overflow) return;
     const int begin = meta->lvl_off[l], count = meta->lvl_cnt[l];
     const int o = threadIdx.x & 7;
     const int g0 = (threadIdx.x & 31) & ~7;
     const unsigned gmask = 0xffu << g0;
-    for (int gt = blockIdx.x * blockDim.x + threadIdx.x; (gt >> 3) < count; gt += gridDim.x * blockDim.x) {   // whole octets
+    for (int gt = bid * blockDim.x + threadIdx.x; (gt >> 3) < count; gt += nblocks * blockDim.x) {   // whole octets
         const ExpRec *r = rec + begin + (gt >> 3);
         const int nch = r->nch, fcid = r->first_child;
         const bool child_level_expandable = (r->level + 1) < MAX_LEVEL;
@@ -309,6 +325,128 @@ __global__ void __launch_bounds__(128) moments_kernel(const ExpRec *__restrict__
             geo[id].cx = __ddiv_rn(sx, tot); geo[id].cy = __ddiv_rn(sy, tot); geo[id].cz = __ddiv_rn(sz, tot);
         }
     }
+}
+
+__global__ void __launch_bounds__(128) moments_kernel(const ExpRec *rec, const TreeMeta *meta, int l, int max_leaf,
+                                                     const double4 *__restrict__ psorted, WalkGeo *geo, WalkTopo *topo, double *mtd)
+{
+    moments_level(rec, meta, l, max_leaf, psorted, geo, topo, mtd, blockIdx.x, gridDim.x);
+}
+
+// ---- the whole build in ONE cooperative launch ------------------------------------------------------------------------
+// Small and medium systems (config 4: N = 60000) spend the build waiting on ~50 launches, half of them for levels the
+// tree does not have.  Here the levels are loops inside one kernel with a grid barrier in between -- the launch is
+// cooperative, so all CTAs are resident and the barrier cannot starve -- and both loops stop where the tree stops:
+// discovery (a barrier per level), the exclusive scan of the children-per-start-position array (three phases), the
+// bookkeeping, the node planes, the moments (a barrier per level).  Same device functions as the one-launch-per-level path.
+struct TreeCoopArgs {
+    ExpRec *rec;
+    TreeMeta *meta;
+    const long long *K;
+    const int *perm;
+    const double4 *psorted;
+    const double *box;
+    int *W, *P, *partial;       // W: children created per start position, P: its exclusive scan, partial: per-CTA sums
+    WalkGeo *geo;
+    WalkTopo *topo;
+    double *mtd;
+    unsigned *barrier;          // monotone arrival counter (zeroed before the launch)
+    int n, max_leaf, ne_cap, m_cap, fixed_mode;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();                       // this CTA's writes are visible before it arrives
+        atomicAdd(bar, 1u);
+        unsigned spins = 0;
+        while (*(volatile unsigned *)bar < target) {
+            if (++spins > (1u << 28)) break;   // never in a cooperative launch; bounds a mistake instead of hanging the GPU
+        }
+        __threadfence();                       // also drops this SM's L1 lines: the next phase reads what other SMs wrote
+    }
+    __syncthreads();
+}
+
+constexpr int TREE_COOP_THREADS = EXPAND_THREADS;
+
+__global__ void __launch_bounds__(TREE_COOP_THREADS) tree_coop_kernel(const TreeCoopArgs a)
+{
+    __shared__ int s_scan[TREE_COOP_THREADS / 32];
+    __shared__ int s_carry;
+    unsigned target = 0;
+    const int bid = blockIdx.x, nb = gridDim.x, tid = threadIdx.x;
+    volatile TreeMeta *vm = a.meta;
+
+    // discovery
+    int levels = 1;
+    for (int l = 0; l < MAX_LEVEL; l++) {
+        expand_level(a.rec, a.meta, l, a.K, a.max_leaf, a.W, a.ne_cap, bid, nb);
+        grid_barrier(a.barrier, target);
+        levels = l + 1;
+        if (vm->lvl_cnt[l + 1] == 0) break;     // the same value on every CTA (read after the barrier)
+    }
+
+    // numbering: P = exclusive scan of W[0..n]; every CTA owns one contiguous chunk
+    const int total = a.n + 1;
+    const int chunk = ((total + nb - 1) / nb + TREE_COOP_THREADS - 1) / TREE_COOP_THREADS * TREE_COOP_THREADS;
+    const int c0 = min(bid * chunk, total), c1 = min(c0 + chunk, total);
+    auto block_sum = [&](int v) -> int {        // total over the CTA, valid on every thread
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        __syncthreads();
+        if ((tid & 31) == 0) s_scan[tid >> 5] = v;
+        __syncthreads();
+        int t = 0;
+        for (int w = 0; w < TREE_COOP_THREADS / 32; w++) t += s_scan[w];
+        return t;
+    };
+    {
+        int v = 0;
+        for (int i = c0 + tid; i < c1; i += TREE_COOP_THREADS) v += a.W[i];
+        const int t = block_sum(v);
+        if (tid == 0) a.partial[bid] = t;
+    }
+    grid_barrier(a.barrier, target);
+    {
+        // offset of this chunk: sum of the partials of the CTAs before it (nb <= a few hundred: one strided pass)
+        int v = 0;
+        for (int b = tid; b < bid; b += TREE_COOP_THREADS) v += ((volatile int *)a.partial)[b];
+        int carry = block_sum(v);
+        for (int i0 = c0; i0 < c1; i0 += TREE_COOP_THREADS) {
+            const int i = i0 + tid;
+            const int w = (i < c1) ? a.W[i] : 0;
+            int inc = w;                          // inclusive scan over the CTA
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((tid & 31) >= d) inc += t;
+            }
+            __syncthreads();
+            if ((tid & 31) == 31) s_scan[tid >> 5] = inc;
+            __syncthreads();
+            int before = 0, all = 0;
+            for (int q = 0; q < TREE_COOP_THREADS / 32; q++) {
+                const int t = s_scan[q];
+                if (q < (tid >> 5)) before += t;
+                all += t;
+            }
+            if (i < c1) a.P[i] = carry + before + inc - w;
+            carry += all;
+        }
+    }
+    grid_barrier(a.barrier, target);
+    if (bid == 0 && tid == 0) tree_meta_body(a.meta, a.P, a.n, a.box, a.ne_cap, a.m_cap);
+    grid_barrier(a.barrier, target);
+    fill_nodes_body(a.rec, a.meta, a.n, a.max_leaf, a.P, a.K, a.perm, a.fixed_mode, a.geo, a.topo, bid, nb);
+    grid_barrier(a.barrier, target);
+    for (int l = levels - 1; l >= 0; l--) {
+        moments_level(a.rec, a.meta, l, a.max_leaf, a.psorted, a.geo, a.topo, a.mtd, bid, nb);
+        if (l > 0) grid_barrier(a.barrier, target);
+    }
+    (void)s_carry;
 }
 
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const double4 *__restrict__ posm, const int *__restrict__ perm, int n,
@@ -386,8 +524,46 @@ int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double bo
     GB_LAUNCH_CHECK();
     count_launch(2);
 
-    // discovery: level l holds at most min(8^l, n / (max_leaf + 1)) expanded nodes
+    // Single cooperative launch (levels as loops with grid barriers) unless the system is large enough for launch overheads
+    // not to matter, the device refuses the cooperative grid, or GRAV_B200_TREE_KERNEL=levels asks for one launch per level.
     const long long most = (long long)n / (max_leaf + 1) + 1;
+    static const char *tree_env = getenv("GRAV_B200_TREE_KERNEL");
+    bool coop = tree_env ? strcmp(tree_env, "coop") == 0 : n <= (1 << 22);
+    if (coop) {
+        if (c->tree_coop_ctas < 0) {
+            int per_sm = 0;
+            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_coop_kernel, TREE_COOP_THREADS, 0));
+            c->tree_coop_ctas = per_sm * c->sm_count;
+        }
+        int grid = grid_for(most * 8, TREE_COOP_THREADS, c->sm_count * 4);
+        if (grid > c->tree_coop_ctas) grid = c->tree_coop_ctas;
+        if (grid < 1) coop = false;
+        if (coop) {
+            GB_TRY(t.scan_tmp.reserve(sizeof(int) * ((size_t)grid + 16)));
+            TreeCoopArgs ta{};
+            ta.rec = rec; ta.meta = meta; ta.K = K; ta.perm = t.perm.as<int>(); ta.psorted = t.posm_sorted.as<double4>();
+            ta.box = t.bbox.as<double>() + 8;
+            ta.W = t.wsum.as<int>(); ta.P = t.wscan.as<int>(); ta.partial = t.scan_tmp.as<int>();
+            ta.geo = geo; ta.topo = topo; ta.mtd = t.node_mtd.as<double>();
+            ta.barrier = &meta->coop_barrier;
+            ta.n = n; ta.max_leaf = max_leaf; ta.ne_cap = t.ne_cap; ta.m_cap = t.m_cap;
+            ta.fixed_mode = c->bh_mode == GRAV_B200_BH_FIXED ? 1 : 0;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(TREE_COOP_THREADS);
+            cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeCooperative;
+            at[0].val.cooperative = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            const cudaError_t e = cudaLaunchKernelEx(&cfg, tree_coop_kernel, ta);
+            if (e == cudaErrorCooperativeLaunchTooLarge) { cudaGetLastError(); coop = false; }
+            else { GB_CUDA(e); count_launch(); }
+        }
+    }
+    if (!coop) {
+    // discovery: level l holds at most min(8^l, n / (max_leaf + 1)) expanded nodes
     long long pow8 = 1;
     for (int l = 0; l < MAX_LEVEL; l++) {
         const long long ub = pow8 < most ? pow8 : most;
@@ -415,6 +591,7 @@ int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double bo
                                                                                         geo, topo, t.node_mtd.as<double>());
         GB_LAUNCH_CHECK();
         count_launch();
+    }
     }
     GB_CUDA(cudaMemcpyAsync(t.h_meta, meta, sizeof(TreeMeta), cudaMemcpyDeviceToHost, c->stream));
     t.built = true;

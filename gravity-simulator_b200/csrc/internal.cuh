@@ -110,6 +110,8 @@ struct TreeMeta {
     int num_nodes;      // M = 1 + children of all expanded nodes
     int levels;         // levels that hold expanded nodes
     int overflow;       // bit 0: more expanded nodes than exp_rec holds, bit 1: more nodes than the node planes hold
+    unsigned coop_barrier;   // arrival counter of the single-launch build's grid barrier
+    unsigned pad_;
     double box_width;
     double cell2[24];   // (box_length / (2 << level))^2 per child level, src/acceleration_barnes_hut.c:157,162
 };
@@ -176,6 +178,7 @@ struct grav_b200_ctx {
     void *wh = nullptr;   // gb::WhfastState (whfast_resident.cu)
     // per-device launch state of the radix sort (bh_sort.cu)
     int sort_resident_ctas = -1;
+    int tree_coop_ctas = -1;          // co-resident CTAs of the single-launch tree build on this device (bh_build.cu)
     bool sort_attr_scatter = false, sort_attr_onesweep = false;
 
     int bh_mode = 0;

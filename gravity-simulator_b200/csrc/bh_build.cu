@@ -535,7 +535,9 @@ int bh_build(grav_b200_ctx *c, int max_leaf, const double *box_center, double bo
             GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_coop_kernel, TREE_COOP_THREADS, 0));
             c->tree_coop_ctas = per_sm * c->sm_count;
         }
-        int grid = grid_for(most * 8, TREE_COOP_THREADS, c->sm_count * 4);
+        static const int ctas_env = getenv("GRAV_B200_TREE_CTAS") ? atoi(getenv("GRAV_B200_TREE_CTAS")) : 0;
+        // measured (profiles/r2_tree_coop_grid.txt): N = 60000 is fastest with 2 CTAs per SM (0.21 ms), N = 2^20 with 4 or more
+        int grid = grid_for(most * 8, TREE_COOP_THREADS, ctas_env > 0 ? ctas_env : c->sm_count * (n <= (1 << 17) ? 2 : 4));
         if (grid > c->tree_coop_ctas) grid = c->tree_coop_ctas;
         if (grid < 1) coop = false;
         if (coop) {

@@ -41,6 +41,14 @@ for integ in ("euler", "euler_cromer", "rk4"):
         c.fixed_steps(1e-3, 2)
         c.positions(); c.velocities()
 gb.compute_energy(x, v, m, G)
+# round 2: the exact per-lane walk and the one-launch-per-level build beside the defaults (cooperative walk, single-launch
+# build); a coincident pair through the energy fallback; the mailbox path already ran for n = 9 above
+abi, _ = gb.load()
+abi.grav_b200_set_bh_exact(1)
+gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)
+abi.grav_b200_set_bh_exact(0)
+xc = x.copy(); xc[3] = xc[700]
+gb.compute_energy(xc, v, m, G)
 x, v, m, G = ics.plummer(40000, 1)
 gb.acceleration(x, m, G, "pairwise", 0.01)      # fast kernel + fix-up + special-tile kernel
 gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)

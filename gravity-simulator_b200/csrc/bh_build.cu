@@ -55,10 +55,10 @@ int radix_sort_pairs(grav_b200_ctx *c);
 
 __global__ void tree_init_kernel(ExpRec *rec, TreeMeta *meta, int n)
 {
-    if (threadIdx.x < 24) {
-        meta->lvl_cnt[threadIdx.x] = threadIdx.x == 0 ? 1 : 0;
-        meta->lvl_off[threadIdx.x] = 0;
-    }
+    // every word of the bookkeeping starts defined (the whole struct is copied to the host at the end of the build)
+    for (int w = threadIdx.x; w < (int)(sizeof(TreeMeta) / sizeof(int)); w += blockDim.x) reinterpret_cast<int *>(meta)[w] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) meta->lvl_cnt[0] = 1;
     if (threadIdx.x == 0) {
         meta->num_expanded = 0; meta->num_nodes = 0; meta->levels = 0; meta->overflow = 0; meta->coop_barrier = 0;
         ExpRec r;

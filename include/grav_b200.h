@@ -211,7 +211,11 @@ int grav_b200_ctx_fixed_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
  *                   first brings the velocities back by half a step, as the reference does before an output
  *                   (:346-351) -- and like the reference leaves x/v in that state; snapshot == 0 returns what the
  *                   last step left (v from the half-step Jacobi velocities), the reference's state at loop exit.
- *   whfast_end():   releases the integrator state. */
+ *   whfast_end():   releases the integrator state.
+ * Ordering assumptions behind "bit-identical": equal distances keep index order (stable sort -- glibc's qsort is a stable
+ * merge sort for these sizes; the C standard leaves tie order open) and invalid particles are removed in ascending index
+ * order (the reference's serial order; its OpenMP build fills the removal list in thread-arrival order).  The reference's
+ * verbose-mode diagnostics of whfast_drift are not printed by this loop. */
 int grav_b200_ctx_whfast_begin(grav_b200_ctx *ctx, const int *particle_ids, int method, double softening_length,
                                double dt, int remove_invalid_particles);
 int grav_b200_ctx_whfast_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);

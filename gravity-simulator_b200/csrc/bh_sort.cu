@@ -771,8 +771,14 @@ int radix_sort_small(grav_b200_ctx *c, long long *ka, int *pa, long long *kb, in
     cudaLaunchAttribute coop[1];
     coop[0].id = cudaLaunchAttributeCooperative;
     coop[0].val.cooperative = 1;
+    static const bool coop_off = getenv("GRAV_B200_SORT_COOP") && atoi(getenv("GRAV_B200_SORT_COOP")) == 0;   // A/B only
+    // Not inside a stream capture: graphs with cooperative kernel nodes made every new WHFast context slower than the last
+    // (launch_simulation_python of config 3: 87, 242, 639 ms for the same 400 steps; 80 ms flat without).  A captured launch is
+    // replayed by the graph on this context's stream like the plain launch it was in round 1.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    GB_CUDA(cudaStreamIsCapturing(c->stream, &cap));
     cfg.attrs = coop;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (coop_off || cap != cudaStreamCaptureStatusNone) ? 0 : 1;
     static const bool per_pass = getenv("GRAV_B200_SORT_SMALL_PER_PASS") && atoi(getenv("GRAV_B200_SORT_SMALL_PER_PASS")) != 0;
     if (!per_pass) {
         unsigned *barrier = status + words - 8;

@@ -478,11 +478,11 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_kernel(const long 
 constexpr unsigned SMALL_VALID = 0x80000000u;
 constexpr int SMALL_MAX_TILES = 128;
 
-template <int ROUNDS>
-__global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const long long *__restrict__ keys_in,
-                                                                       const int *__restrict__ vals_in, int n, int shift,
-                                                                       int num_tiles, unsigned *__restrict__ status,
-                                                                       long long *__restrict__ keys_out, int *__restrict__ vals_out)
+// One pass of one tile; shared by the one-pass kernel and the all-passes kernel below.  CROSS: the input was written by
+// other CTAs earlier in this launch, so it is read past L1 (__ldcg).
+template <int ROUNDS, bool CROSS>
+__device__ __forceinline__ void sort_small_tile_pass(const long long *keys_in, const int *vals_in, int n, int shift, int num_tiles,
+                                                     unsigned *status, long long *keys_out, int *vals_out)
 {
     constexpr int TILE = SORT_THREADS * ROUNDS;
     constexpr int WCHUNK = 32 * ROUNDS;
@@ -508,8 +508,8 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const lon
     for (int r = 0; r < ROUNDS; r++) {
         const int li = wbase + r * 32 + lane;
         const bool valid = li < tile_n;
-        k[r] = valid ? keys_in[base + li] : 0;
-        v[r] = valid ? vals_in[base + li] : 0;
+        k[r] = valid ? (CROSS ? __ldcg(keys_in + base + li) : keys_in[base + li]) : 0;
+        v[r] = valid ? (CROSS ? __ldcg(vals_in + base + li) : vals_in[base + li]) : 0;
     }
 #pragma unroll
     for (int r = 0; r < ROUNDS; r++) {
@@ -595,139 +595,36 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const lon
     }
 }
 
+template <int ROUNDS>
+__global__ void __launch_bounds__(SORT_THREADS) sort_small_pass_kernel(const long long *keys_in, const int *vals_in, int n, int shift,
+                                                                       int num_tiles, unsigned *status, long long *keys_out,
+                                                                       int *vals_out)
+{
+    sort_small_tile_pass<ROUNDS, false>(keys_in, vals_in, n, shift, num_tiles, status, keys_out, vals_out);
+}
+
 // The same eight passes inside ONE kernel: the wait for all tiles' counts already is a grid-wide rendezvous, a second
 // one (atomic arrival counter) after the scatter lets the next pass start without a kernel boundary.  All CTAs are
-// resident (<= 128), so the barriers cannot deadlock.  A graph node costs ~6 us on this path, a barrier ~2 us.
+// resident (<= 128; launched cooperatively outside graph captures), so the barriers cannot deadlock.  A graph node costs
+// ~6 us on this path, a barrier ~2 us.
 template <int ROUNDS>
 __global__ void __launch_bounds__(SORT_THREADS) sort_small_all_kernel(long long *ka, int *pa, long long *kb, int *pb, int n, int num_tiles, unsigned *status_all,
                                                                       unsigned *bar)
 {
-    constexpr int TILE = SORT_THREADS * ROUNDS;
-    constexpr int WCHUNK = 32 * ROUNDS;
-    __shared__ long long skeys[TILE];
-    __shared__ int svals[TILE];
-    __shared__ int wcnt[SORT_WARPS][SORT_RADIX];
-    __shared__ int gbase[SORT_RADIX];
-    __shared__ int wsum[SORT_WARPS], wsum2[SORT_WARPS];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int tile = blockIdx.x;
-    const int base = tile * TILE;
-    const int tile_n = min(TILE, n - base);
-  for (int pass = 0; pass < 8; pass++) {
-    // buffers alternate; pairs written by other CTAs during the previous pass are read past L1 (__ldcg)
-    const long long *keys_in = (pass & 1) ? kb : ka;
-    const int *vals_in = (pass & 1) ? pb : pa;
-    long long *keys_out = (pass & 1) ? ka : kb;
-    int *vals_out = (pass & 1) ? pa : pb;
-    unsigned *status = status_all + (size_t)pass * SMALL_MAX_TILES * SORT_RADIX;
-    const int shift = pass * SORT_BITS;
-    for (int d = lane; d < SORT_RADIX; d += 32) wcnt[warp][d] = 0;
-    __syncwarp();
-
-    long long k[ROUNDS];
-    int v[ROUNDS];
-    unsigned short rk[ROUNDS];
-    const int wbase = warp * WCHUNK;
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        const int li = wbase + r * 32 + lane;
-        const bool valid = li < tile_n;
-        k[r] = valid ? __ldcg(keys_in + base + li) : 0;
-        v[r] = valid ? __ldcg(vals_in + base + li) : 0;
-    }
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        const int li = wbase + r * 32 + lane;
-        const bool valid = li < tile_n;
-        const int d = valid ? digit_of(k[r], shift) : SORT_RADIX;
-        const unsigned same = __match_any_sync(0xffffffffu, d);
-        const int leader = 31 - __clz(same);
-        int prev = 0;
-        if (valid && lane == leader) {
-            prev = wcnt[warp][d];
-            wcnt[warp][d] = prev + __popc(same);
-        }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        rk[r] = (unsigned short)(prev + __popc(same & lt));
-        __syncwarp();
-    }
-    __syncthreads();
-
-    {
-        const int d = tid;
-        int run = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            const int t = wcnt[w][d];
-            wcnt[w][d] = run;
-            run += t;
-        }
-        st_status(status + (size_t)tile * SORT_RADIX + d, (unsigned)run | SMALL_VALID);
-        // every tile's count of digit d ([tile][digit] layout: a warp reads 128 contiguous bytes per tile): batches of 32
-        // independent loads (one L2 round trip each batch), then spin only on the stragglers
-        int tot = 0, before = 0;
-        for (int t0 = 0; t0 < num_tiles; t0 += 32) {
-            unsigned w16[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) w16[j] = (t0 + j < num_tiles) ? ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d) : SMALL_VALID;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                unsigned sv = w16[j];
-                while (!(sv & SMALL_VALID)) sv = ld_status(status + (size_t)(t0 + j) * SORT_RADIX + d);
-                const int h = (int)(sv & ~SMALL_VALID);
-                tot += h;
-                if (t0 + j < tile) before += h;
-            }
-        }
-        int inc = run, ginc = tot;
-#pragma unroll
-        for (int s2 = 1; s2 < 32; s2 <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, s2);
-            const int g = __shfl_up_sync(0xffffffffu, ginc, s2);
-            if (lane >= s2) { inc += t; ginc += g; }
-        }
-        if (lane == 31) { wsum[warp] = inc; wsum2[warp] = ginc; }
+    for (int pass = 0; pass < 8; pass++) {
+        // buffers alternate
+        sort_small_tile_pass<ROUNDS, true>((pass & 1) ? kb : ka, (pass & 1) ? pb : pa, n, pass * SORT_BITS, num_tiles,
+                                           status_all + (size_t)pass * SMALL_MAX_TILES * SORT_RADIX, (pass & 1) ? ka : kb,
+                                           (pass & 1) ? pa : pb);
+        // grid barrier: every tile's output must be in memory before anybody reads it as the next pass's input
+        __threadfence();
         __syncthreads();
-        int woff = 0, goff = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            woff += (w < warp) ? wsum[w] : 0;
-            goff += (w < warp) ? wsum2[w] : 0;
+        if (threadIdx.x == 0) {
+            atomicAdd(bar + pass, 1u);
+            while (ld_status(bar + pass) < (unsigned)num_tiles) { }
         }
-        const int dstart = woff + inc - run;
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) wcnt[w][d] += dstart;
-        gbase[d] = (goff + ginc - tot) + before - dstart;
+        __syncthreads();
     }
-    __syncthreads();
-
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        const int li = wbase + r * 32 + lane;
-        if (li < tile_n) {
-            const int slot = wcnt[warp][digit_of(k[r], shift)] + rk[r];
-            skeys[slot] = k[r];
-            svals[slot] = v[r];
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < tile_n; i += SORT_THREADS) {
-        const long long kk = skeys[i];
-        const int pos = gbase[digit_of(kk, shift)] + i;
-        keys_out[pos] = kk;
-        vals_out[pos] = svals[i];
-    }
-    // grid barrier: every tile's output must be in memory before anybody reads it as the next pass's input
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        atomicAdd(bar + pass, 1u);
-        while (ld_status(bar + pass) < (unsigned)num_tiles) { }
-    }
-    __syncthreads();
-  }
 }
 
 int radix_pass(grav_b200_ctx *c, const long long *kin, const int *vin, long long *kout, int *vout, int n, int shift);

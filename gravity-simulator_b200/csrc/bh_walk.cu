@@ -109,6 +109,9 @@ __device__ __forceinline__ void eval_fast(double sx, double sy, double sz, doubl
 #ifndef CW_SYNC
 #define CW_SYNC 0
 #endif
+#ifndef CW_OPAQUE
+#define CW_OPAQUE 0     // 1: ~18 fewer instructions per trip (105 vs 123) and 0.7 ms SLOWER: the walk is latency bound, the rematerialised address arithmetic fills idle issue slots (profiles/r2_walk_opaque_ab.txt)
+#endif
 constexpr int CW_WARPS = CW_WARPS_DEF;       // warps per CTA
 constexpr int CW_STACK = 512;     // stack entries per warp (4 bytes each: first child id << 4 | number of children)
 // Above CW_HIGH entries the warp pops ONE opened node per trip, i.e. walks depth-first, where the stack grows by at most
@@ -125,10 +128,26 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) walk_coop_kernel(const
     __shared__ unsigned s_stack[CW_WARPS][CW_STACK];
     if (a.meta->overflow) return;   // the build did not fit its buffers: the planes are not a tree (reported by the host)
     const int lane = threadIdx.x & 31;
+#if CW_OPAQUE
+    // Per-lane constants handed to the compiler as opaque register values: under the 64-register cap ptxas otherwise
+    // rematerialises them from SR_TID / SR_CgaCtaId on every trip (~20 of 123 instructions, profiles/r2_walk_coop_v2_n1m.txt).
+    unsigned stk_s, e_o, k_o, lt_o;
+    asm volatile("mov.u32 %0, %1;" : "=r"(stk_s) : "r"((unsigned)__cvta_generic_to_shared(s_stack[threadIdx.x >> 5])));
+    asm volatile("mov.u32 %0, %1;" : "=r"(e_o) : "r"((unsigned)(lane >> 3)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(k_o) : "r"((unsigned)(lane & 7)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(lt_o) : "r"((1u << lane) - 1u));
+    const int e = (int)e_o;
+    const unsigned k = k_o, lt = lt_o;
+#define STK_ST(idx, val) asm volatile("st.shared.u32 [%0], %1;" ::"r"(stk_s + 4u * (unsigned)(idx)), "r"(val) : "memory")
+#define STK_LD(dst, idx) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dst) : "r"(stk_s + 4u * (unsigned)(idx)) : "memory")
+#else
     unsigned *const stk = s_stack[threadIdx.x >> 5];
     const int e = lane >> 3;
     const unsigned k = lane & 7;
     const unsigned lt = (1u << lane) - 1u;
+#define STK_ST(idx, val) stk[idx] = (val)
+#define STK_LD(dst, idx) dst = stk[idx]
+#endif
     const unsigned root_ent = __ldg(&a.topo[0].fcn);   // the root is always expanded
     const long long t0 = ((long long)blockIdx.x * CW_WARPS + (threadIdx.x >> 5)) * tpw;
     for (int tt = 0; tt < tpw; tt++) {
@@ -190,13 +209,13 @@ __global__ void __launch_bounds__(CW_WARPS * 32, CW_MINB) walk_coop_kernel(const
                 }
             }
             const unsigned om = __ballot_sync(0xffffffffu, open);
-            if (open) stk[sp + __popc(om & lt)] = child_ent;
+            if (open) STK_ST(sp + __popc(om & lt), child_ent);
             sp += __popc(om);
             __syncwarp();
             // next batch: its record loads are in flight while this trip's sources are evaluated
             const bool more = sp > 0;
             const int take = sp > CW_HIGH ? 1 : min(sp, 4);       // 0 when the stack is empty: every lane goes idle
-            ent = stk[max(sp - 1 - e, 0)];
+            STK_LD(ent, max(sp - 1 - e, 0));
             if (e >= take) ent = 0u;
             __syncwarp();
             sp -= take;

@@ -90,6 +90,104 @@ static ErrorStatus status_from_rc(const int rc, const char *file, const int line
         }                                                  \
     } while (0)
 
+/* ---- the time loop shared by every resident integrator ------------------------------------------------------
+ * Bookkeeping of src/integrator.c:996-1086 (leapfrog; euler :351-441, euler_cromer :525-614, rk4 :736-880) and
+ * src/integrator_whfast.c:286-383, which are the same statements: dt overshoot, t = num_steps * dt, output when t passes
+ * the next output time, progress bar, is_exit.  Steps are queued on the device and flushed when the host has to look
+ * (output due, leaving, RESIDENT_MAX_QUEUED_STEPS reached, dt changed). */
+typedef struct ResidentOps
+{
+    int (*steps)(grav_b200_ctx *ctx, double dt, int64_t num_steps);
+    int (*download)(grav_b200_ctx *ctx, System *system, int snapshot);   /* host arrays of `system` <- device state */
+    int (*finish)(grav_b200_ctx *ctx);                                    /* after the last step, before the final download; may be NULL */
+    bool check_overshoot;                                                 /* rk4() has no overshoot check (:736-741) */
+} ResidentOps;
+
+static int download_xv(grav_b200_ctx *ctx, System *system, const int snapshot)
+{
+    (void) snapshot;   /* while a leapfrog runs get_velocities() already applies the snapshot convention (:1045-1073) */
+    const int rc = grav_b200_ctx_get_positions(ctx, system->x);
+    return rc != GRAV_B200_OK ? rc : grav_b200_ctx_get_velocities(ctx, system->v);
+}
+
+static ErrorStatus resident_time_loop(grav_b200_ctx *ctx, const ResidentOps *ops, System *system, IntegratorParam *integrator_param,
+                                      AccelerationParam *acceleration_param, OutputParam *output_param,
+                                      SimulationStatus *simulation_status, Settings *settings, const double tf)
+{
+    ErrorStatus error_status = make_success_error_status();
+    double dt = integrator_param->dt;
+    const bool is_output = (output_param->method != OUTPUT_METHOD_DISABLED);
+    const double output_interval = output_param->output_interval;
+    double next_output_time = output_interval;
+    const bool enable_progress_bar = settings->enable_progress_bar;
+    ProgressBarParam progress_bar_param;
+    int64 queued = 0;
+    double queued_dt = dt;
+
+    const int64 total_num_steps = (int64) ceil(tf / dt);
+    if (enable_progress_bar)
+    {
+        TRY_STATUS(start_progress_bar(&progress_bar_param, total_num_steps));
+    }
+    simulation_status->t = 0.0;
+    simulation_status->dt = dt;
+    simulation_status->num_steps = 0;
+    while (simulation_status->num_steps < total_num_steps)
+    {
+        if (ops->check_overshoot)
+        {
+            if (simulation_status->t + dt > tf)
+            {
+                dt = tf - simulation_status->t;
+            }
+            simulation_status->dt = dt;
+        }
+        if (queued > 0 && dt != queued_dt)
+        {
+            TRY_RC(ops->steps(ctx, queued_dt, queued));
+            queued = 0;
+        }
+        queued_dt = dt;
+        queued++;
+
+        (simulation_status->num_steps)++;
+        simulation_status->t = (simulation_status->num_steps) * dt;
+
+        const bool output_due = is_output && simulation_status->t >= next_output_time;
+        const bool leaving = *(settings->is_exit_ptr) || simulation_status->num_steps == total_num_steps;
+        if (output_due || leaving || queued >= RESIDENT_MAX_QUEUED_STEPS)
+        {
+            TRY_RC(ops->steps(ctx, queued_dt, queued));
+            queued = 0;
+        }
+        if (output_due)
+        {
+            TRY_RC(ops->download(ctx, system, 1));
+            TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
+            next_output_time = (output_param->output_count_) * output_interval;
+        }
+        if (enable_progress_bar)
+        {
+            update_progress_bar(&progress_bar_param, simulation_status->num_steps, false);
+        }
+        if (*(settings->is_exit_ptr))
+        {
+            break;
+        }
+    }
+    if (ops->finish)
+    {
+        TRY_RC(ops->finish(ctx));
+    }
+    TRY_RC(ops->download(ctx, system, 0));
+    if (enable_progress_bar)
+    {
+        update_progress_bar(&progress_bar_param, simulation_status->num_steps, true);
+    }
+done:
+    return error_status;
+}
+
 /* ---- WHFast (src/integrator_whfast.c:200-407) ------------------------------------------------------------- */
 
 static int whfast_download(grav_b200_ctx *ctx, System *system, const int snapshot)
@@ -119,81 +217,23 @@ int grav_b200_shim_whfast(ErrorStatus *out, System *system, IntegratorParam *int
 
     ErrorStatus error_status = make_success_error_status();
     grav_b200_ctx *ctx = NULL;
-    double dt = integrator_param->dt;
-    const bool is_output = (output_param->method != OUTPUT_METHOD_DISABLED);
-    const double output_interval = output_param->output_interval;
-    double next_output_time = output_interval;
-    const bool enable_progress_bar = settings->enable_progress_bar;
-    ProgressBarParam progress_bar_param;
-    int64 queued = 0;
-    double queued_dt = dt;
+    /* the reference leaves system->x / v as its last jacobi_to_cartesian wrote them; so does the final download (snapshot = 0);
+     * outputs between steps use the -dt/2 snapshot convention (:346-366) */
+    const ResidentOps ops = {grav_b200_ctx_whfast_steps, whfast_download, NULL, true};
 
-    TRY_RC(grav_b200_ctx_create(&ctx, resident_device(), 0, 1, NULL));
+    TRY_RC(grav_b200_ctx_create(&ctx, resident_device(), 0, 1, NULL));   /* one GPU by design: DESIGN.md section 5 */
     TRY_RC(grav_b200_ctx_set_system(ctx, system->num_particles, system->x, system->v, system->m, system->G));
     /* sort by distance, eta, Jacobi coordinates, first acceleration, half kick (:241-273) */
     TRY_RC(grav_b200_ctx_whfast_begin(ctx, system->particle_ids, acceleration_param->method,
-                                      acceleration_param->softening_length, dt,
+                                      acceleration_param->softening_length, integrator_param->dt,
                                       integrator_param->whfast_remove_invalid_particles));
     TRY_RC(whfast_download(ctx, system, 0));     /* the distance-sorted system, as the initial output sees it */
-    if (is_output && output_param->output_initial)
+    if (output_param->method != OUTPUT_METHOD_DISABLED && output_param->output_initial)
     {
         TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
     }
-
-    const int64 total_num_steps = (int64) ceil(tf / dt);
-    if (enable_progress_bar)
-    {
-        TRY_STATUS(start_progress_bar(&progress_bar_param, total_num_steps));
-    }
-    simulation_status->t = 0.0;
-    simulation_status->dt = dt;
-    simulation_status->num_steps = 0;
-    while (simulation_status->num_steps < total_num_steps)
-    {
-        if (simulation_status->t + dt > tf)      /* dt overshoot (:293-297) */
-        {
-            dt = tf - simulation_status->t;
-        }
-        simulation_status->dt = dt;
-        if (queued > 0 && dt != queued_dt)
-        {
-            TRY_RC(grav_b200_ctx_whfast_steps(ctx, queued_dt, queued));
-            queued = 0;
-        }
-        queued_dt = dt;
-        queued++;
-
-        (simulation_status->num_steps)++;
-        simulation_status->t = (simulation_status->num_steps) * dt;
-
-        const bool output_due = is_output && simulation_status->t >= next_output_time;
-        const bool leaving = *(settings->is_exit_ptr) || simulation_status->num_steps == total_num_steps;
-        if (output_due || leaving || queued >= RESIDENT_MAX_QUEUED_STEPS)
-        {
-            TRY_RC(grav_b200_ctx_whfast_steps(ctx, queued_dt, queued));
-            queued = 0;
-        }
-        if (output_due)                          /* (:346-366) */
-        {
-            TRY_RC(whfast_download(ctx, system, 1));
-            TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
-            next_output_time = (output_param->output_count_) * output_interval;
-        }
-        if (enable_progress_bar)
-        {
-            update_progress_bar(&progress_bar_param, simulation_status->num_steps, false);
-        }
-        if (*(settings->is_exit_ptr))
-        {
-            break;
-        }
-    }
-    if (enable_progress_bar)
-    {
-        update_progress_bar(&progress_bar_param, simulation_status->num_steps, true);
-    }
-    /* the reference leaves system->x / v as its last jacobi_to_cartesian wrote them; so does the device state */
-    TRY_RC(whfast_download(ctx, system, 0));
+    error_status = resident_time_loop(ctx, &ops, system, integrator_param, acceleration_param, output_param, simulation_status,
+                                      settings, tf);
 
 done:
     if (ctx)
@@ -204,223 +244,72 @@ done:
     return 1;
 }
 
-/* ---- leapfrog (src/integrator.c:894-1121) ------------------------------------------------------------------ */
+/* ---- leapfrog (src/integrator.c:894-1121), Euler, Euler-Cromer, RK4 (:281-454, :456-628, :630-892) ----------- */
+
+/* integrator < 0: leapfrog */
+static int xv_resident(ErrorStatus *out, const int integrator, System *system, IntegratorParam *integrator_param,
+                       AccelerationParam *acceleration_param, OutputParam *output_param, SimulationStatus *simulation_status,
+                       Settings *settings, const double tf)
+{
+    if (!resident_enabled())
+    {
+        return 0;
+    }
+    const int method = acceleration_param->method;
+    if (method != ACCELERATION_METHOD_PAIRWISE && method != ACCELERATION_METHOD_MASSLESS &&
+        method != ACCELERATION_METHOD_BARNES_HUT)
+    {
+        return 0;
+    }
+
+    ErrorStatus error_status = make_success_error_status();
+    grav_b200_ctx *ctx = NULL;
+    const bool is_leapfrog = integrator < 0;
+    /* leapfrog: v_1 from v_1+1/2 for snapshots with the state untouched (:1045-1073), and for good at the end (:1088-1094) */
+    const ResidentOps ops = {is_leapfrog ? grav_b200_ctx_leapfrog_steps : grav_b200_ctx_fixed_steps, download_xv,
+                             is_leapfrog ? grav_b200_ctx_leapfrog_end : NULL, integrator != GRAV_B200_INTEGRATOR_RK4};
+
+    if (output_param->method != OUTPUT_METHOD_DISABLED && output_param->output_initial)       /* (:944-960) */
+    {
+        TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
+    }
+    TRY_RC(grav_b200_ctx_create_auto(&ctx));   /* GRAV_B200_DEVICE, or a team of GRAV_B200_DEVICES GPUs driven from this thread */
+    TRY_RC(grav_b200_ctx_set_system(ctx, system->num_particles, system->x, system->v, system->m, system->G));
+    if (is_leapfrog)
+    {
+        /* a(x0) and v_1/2 (:963-982) */
+        TRY_RC(grav_b200_ctx_leapfrog_begin(ctx, method, acceleration_param->softening_length, acceleration_param->opening_angle,
+                                            acceleration_param->max_num_particles_per_leaf, integrator_param->dt));
+    }
+    else
+    {
+        TRY_RC(grav_b200_ctx_fixed_begin(ctx, integrator, method, acceleration_param->softening_length,
+                                         acceleration_param->opening_angle, acceleration_param->max_num_particles_per_leaf));
+    }
+    error_status = resident_time_loop(ctx, &ops, system, integrator_param, acceleration_param, output_param, simulation_status,
+                                      settings, tf);
+
+done:
+    if (ctx)
+    {
+        grav_b200_ctx_destroy(ctx);
+    }
+    *out = error_status;
+    return 1;
+}
 
 int grav_b200_shim_leapfrog(ErrorStatus *out, System *system, IntegratorParam *integrator_param,
                             AccelerationParam *acceleration_param, OutputParam *output_param,
                             SimulationStatus *simulation_status, Settings *settings, const double tf)
 {
-    if (!resident_enabled())
-    {
-        return 0;
-    }
-    const int method = acceleration_param->method;
-    if (method != ACCELERATION_METHOD_PAIRWISE && method != ACCELERATION_METHOD_MASSLESS &&
-        method != ACCELERATION_METHOD_BARNES_HUT)
-    {
-        return 0;
-    }
-
-    ErrorStatus error_status = make_success_error_status();
-    grav_b200_ctx *ctx = NULL;
-    double dt = integrator_param->dt;
-    const bool is_output = (output_param->method != OUTPUT_METHOD_DISABLED);
-    const double output_interval = output_param->output_interval;
-    double next_output_time = output_interval;
-    const bool enable_progress_bar = settings->enable_progress_bar;
-    ProgressBarParam progress_bar_param;
-    int64 queued = 0;
-    double queued_dt = dt;
-
-    if (is_output && output_param->output_initial)       /* (:944-960) */
-    {
-        TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
-    }
-    TRY_RC(grav_b200_ctx_create_auto(&ctx));   /* GRAV_B200_DEVICE, or a team of GRAV_B200_DEVICES GPUs driven from this thread */
-    TRY_RC(grav_b200_ctx_set_system(ctx, system->num_particles, system->x, system->v, system->m, system->G));
-    /* a(x0) and v_1/2 (:963-982) */
-    TRY_RC(grav_b200_ctx_leapfrog_begin(ctx, method, acceleration_param->softening_length, acceleration_param->opening_angle,
-                                        acceleration_param->max_num_particles_per_leaf, dt));
-
-    const int64 total_num_steps = (int64) ceil(tf / dt);
-    if (enable_progress_bar)
-    {
-        TRY_STATUS(start_progress_bar(&progress_bar_param, total_num_steps));
-    }
-    simulation_status->t = 0.0;
-    simulation_status->dt = dt;
-    simulation_status->num_steps = 0;
-    while (simulation_status->num_steps < total_num_steps)
-    {
-        if (simulation_status->t + dt > tf)
-        {
-            dt = tf - simulation_status->t;
-        }
-        simulation_status->dt = dt;
-        if (queued > 0 && dt != queued_dt)
-        {
-            TRY_RC(grav_b200_ctx_leapfrog_steps(ctx, queued_dt, queued));
-            queued = 0;
-        }
-        queued_dt = dt;
-        queued++;
-
-        (simulation_status->num_steps)++;
-        simulation_status->t = (simulation_status->num_steps) * dt;
-
-        const bool output_due = is_output && simulation_status->t >= next_output_time;
-        const bool leaving = *(settings->is_exit_ptr) || simulation_status->num_steps == total_num_steps;
-        if (output_due || leaving || queued >= RESIDENT_MAX_QUEUED_STEPS)
-        {
-            TRY_RC(grav_b200_ctx_leapfrog_steps(ctx, queued_dt, queued));
-            queued = 0;
-        }
-        if (output_due)      /* v_1 from v_1+1/2 for the snapshot, state untouched (:1045-1073) */
-        {
-            TRY_RC(grav_b200_ctx_get_positions(ctx, system->x));
-            TRY_RC(grav_b200_ctx_get_velocities(ctx, system->v));
-            TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
-            next_output_time = (output_param->output_count_) * output_interval;
-        }
-        if (enable_progress_bar)
-        {
-            update_progress_bar(&progress_bar_param, simulation_status->num_steps, false);
-        }
-        if (*(settings->is_exit_ptr))
-        {
-            break;
-        }
-    }
-    /* synchronise v_1+1/2 to v_1 (:1088-1094) and hand the state back */
-    TRY_RC(grav_b200_ctx_leapfrog_end(ctx));
-    TRY_RC(grav_b200_ctx_get_positions(ctx, system->x));
-    TRY_RC(grav_b200_ctx_get_velocities(ctx, system->v));
-    if (enable_progress_bar)
-    {
-        update_progress_bar(&progress_bar_param, simulation_status->num_steps, true);
-    }
-
-done:
-    if (ctx)
-    {
-        grav_b200_ctx_destroy(ctx);
-    }
-    *out = error_status;
-    return 1;
-}
-
-
-/* ---- Euler, Euler-Cromer, RK4 (src/integrator.c:281-454, :456-628, :630-892) --------------------------------- */
-
-static int fixed_step_resident(ErrorStatus *out, const int integrator, System *system, IntegratorParam *integrator_param,
-                               AccelerationParam *acceleration_param, OutputParam *output_param,
-                               SimulationStatus *simulation_status, Settings *settings, const double tf)
-{
-    if (!resident_enabled())
-    {
-        return 0;
-    }
-    const int method = acceleration_param->method;
-    if (method != ACCELERATION_METHOD_PAIRWISE && method != ACCELERATION_METHOD_MASSLESS &&
-        method != ACCELERATION_METHOD_BARNES_HUT)
-    {
-        return 0;
-    }
-
-    ErrorStatus error_status = make_success_error_status();
-    grav_b200_ctx *ctx = NULL;
-    double dt = integrator_param->dt;
-    const bool is_output = (output_param->method != OUTPUT_METHOD_DISABLED);
-    const double output_interval = output_param->output_interval;
-    double next_output_time = output_interval;
-    const bool enable_progress_bar = settings->enable_progress_bar;
-    const bool check_overshoot = (integrator != GRAV_B200_INTEGRATOR_RK4);   /* rk4() has no overshoot check (:736-741) */
-    ProgressBarParam progress_bar_param;
-    int64 queued = 0;
-    double queued_dt = dt;
-
-    if (is_output && output_param->output_initial)
-    {
-        TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
-    }
-    TRY_RC(grav_b200_ctx_create_auto(&ctx));   /* GRAV_B200_DEVICE, or a team of GRAV_B200_DEVICES GPUs driven from this thread */
-    TRY_RC(grav_b200_ctx_set_system(ctx, system->num_particles, system->x, system->v, system->m, system->G));
-    TRY_RC(grav_b200_ctx_fixed_begin(ctx, integrator, method, acceleration_param->softening_length,
-                                     acceleration_param->opening_angle, acceleration_param->max_num_particles_per_leaf));
-
-    const int64 total_num_steps = (int64) ceil(tf / dt);
-    if (enable_progress_bar)
-    {
-        TRY_STATUS(start_progress_bar(&progress_bar_param, total_num_steps));
-    }
-    simulation_status->t = 0.0;
-    simulation_status->dt = dt;
-    simulation_status->num_steps = 0;
-    while (simulation_status->num_steps < total_num_steps)
-    {
-        if (check_overshoot)
-        {
-            if (simulation_status->t + dt > tf)
-            {
-                dt = tf - simulation_status->t;
-            }
-            simulation_status->dt = dt;
-        }
-        if (queued > 0 && dt != queued_dt)
-        {
-            TRY_RC(grav_b200_ctx_fixed_steps(ctx, queued_dt, queued));
-            queued = 0;
-        }
-        queued_dt = dt;
-        queued++;
-
-        (simulation_status->num_steps)++;
-        simulation_status->t = (simulation_status->num_steps) * dt;
-
-        const bool output_due = is_output && simulation_status->t >= next_output_time;
-        const bool leaving = *(settings->is_exit_ptr) || simulation_status->num_steps == total_num_steps;
-        if (output_due || leaving || queued >= RESIDENT_MAX_QUEUED_STEPS)
-        {
-            TRY_RC(grav_b200_ctx_fixed_steps(ctx, queued_dt, queued));
-            queued = 0;
-        }
-        if (output_due)
-        {
-            TRY_RC(grav_b200_ctx_get_positions(ctx, system->x));
-            TRY_RC(grav_b200_ctx_get_velocities(ctx, system->v));
-            TRY_STATUS(output_snapshot(output_param, system, integrator_param, acceleration_param, simulation_status, settings));
-            next_output_time = (output_param->output_count_) * output_interval;
-        }
-        if (enable_progress_bar)
-        {
-            update_progress_bar(&progress_bar_param, simulation_status->num_steps, false);
-        }
-        if (*(settings->is_exit_ptr))
-        {
-            break;
-        }
-    }
-    TRY_RC(grav_b200_ctx_get_positions(ctx, system->x));
-    TRY_RC(grav_b200_ctx_get_velocities(ctx, system->v));
-    if (enable_progress_bar)
-    {
-        update_progress_bar(&progress_bar_param, simulation_status->num_steps, true);
-    }
-
-done:
-    if (ctx)
-    {
-        grav_b200_ctx_destroy(ctx);
-    }
-    *out = error_status;
-    return 1;
+    return xv_resident(out, -1, system, integrator_param, acceleration_param, output_param, simulation_status, settings, tf);
 }
 
 int grav_b200_shim_euler(ErrorStatus *out, System *system, IntegratorParam *integrator_param,
                          AccelerationParam *acceleration_param, OutputParam *output_param,
                          SimulationStatus *simulation_status, Settings *settings, const double tf)
 {
-    return fixed_step_resident(out, GRAV_B200_INTEGRATOR_EULER, system, integrator_param, acceleration_param, output_param,
+    return xv_resident(out, GRAV_B200_INTEGRATOR_EULER, system, integrator_param, acceleration_param, output_param,
                                simulation_status, settings, tf);
 }
 
@@ -428,7 +317,7 @@ int grav_b200_shim_euler_cromer(ErrorStatus *out, System *system, IntegratorPara
                                 AccelerationParam *acceleration_param, OutputParam *output_param,
                                 SimulationStatus *simulation_status, Settings *settings, const double tf)
 {
-    return fixed_step_resident(out, GRAV_B200_INTEGRATOR_EULER_CROMER, system, integrator_param, acceleration_param,
+    return xv_resident(out, GRAV_B200_INTEGRATOR_EULER_CROMER, system, integrator_param, acceleration_param,
                                output_param, simulation_status, settings, tf);
 }
 
@@ -436,7 +325,7 @@ int grav_b200_shim_rk4(ErrorStatus *out, System *system, IntegratorParam *integr
                        AccelerationParam *acceleration_param, OutputParam *output_param,
                        SimulationStatus *simulation_status, Settings *settings, const double tf)
 {
-    return fixed_step_resident(out, GRAV_B200_INTEGRATOR_RK4, system, integrator_param, acceleration_param, output_param,
+    return xv_resident(out, GRAV_B200_INTEGRATOR_RK4, system, integrator_param, acceleration_param, output_param,
                                simulation_status, settings, tf);
 }
 

@@ -40,9 +40,12 @@ sys.path.insert(0, str(ROOT / "tests"))
 METRIC = "fp64_direct_sum_pair_interactions_per_s"
 UNIT = "G interactions/s"
 FLOP_PER_INTERACTION = 20      # GPU-Gems-3 convention: 18 + rsqrt counted as 2
-FP64_OPS_PER_INTERACTION = 16  # FP64-pipe instructions our kernel actually issues per interaction
+# FP64-pipe instructions the kernels actually issue per ORDERED interaction: 16 in the ordered-interaction kernel
+# (direct_sum.cu); the pair-once kernel (direct_sum_sym.cu) spends 20 per unordered pair = 10 (18 = 9 with equal masses)
+FP64_OPS = {"ordered": 16.0, "pair_once": 10.0, "pair_once_equal_mass": 9.0}
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12   # 37.2, used only if the live measurement fails
-NCU_DRAM_BYTES_PER_LAUNCH = 52571392 + 51328512   # dram read + write, profiles/r1_direct_sum_n1m_final.txt
+NCU_DRAM_BYTES_PER_LAUNCH = {"ordered": 52571392 + 51328512,   # dram read + write, profiles/r1_direct_sum_n1m_final.txt
+                             "pair_once": None}                 # filled from profiles/r2_sym_n1m.txt when that capture exists
 
 
 def parse_args():
@@ -426,16 +429,26 @@ def run_b200_arm(args):
     except Exception as e:  # pragma: no cover
         peak_tf, peak_mhz, peak_src = NOMINAL_FP64_TFLOPS, 1965.0, f"nominal fallback ({e})"
     ach_tf = FLOP_PER_INTERACTION * k_inter / (k_ms * 1e-3) / 1e12
+    pair_once, equal_mass = ctx.direct_sum_path()
+    path = ("pair_once_equal_mass" if equal_mass else "pair_once") if pair_once else "ordered"
+    ops = FP64_OPS[path]
+    traffic = sym_ncu_traffic() if pair_once else NCU_DRAM_BYTES_PER_LAUNCH["ordered"]
     roofline = {
         "bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and n == (1 << 20)) else None,
-        "traffic_note": "dram__bytes_read+write of one launch at N=2^20, ncu --set full (profiles/r1_direct_sum_n1m_final.txt; includes the 28 MB of partial sums of split target blocks); "
-                        "algorithmic bytes = 32 B x N sources + 24 B x N results = 58.7 MB",
-        "kernel": "direct_sum_kernel<4,false,false> (+ the fix-up kernel of split target blocks, <0.1% of the stage)", "kernel_ms": k_ms,
-        "convention": f"{FLOP_PER_INTERACTION} flop per ordered interaction; peak = {peak_src} "
-                      f"(= {peak_mhz:.0f} MHz x 148 SM x 64 DFMA lanes x 2)",
-        "fp64_pipe_util": FP64_OPS_PER_INTERACTION * k_inter / (k_ms * 1e-3) / (peak_tf * 1e12 / 2.0),
-        "fp64_pipe_util_note": f"{FP64_OPS_PER_INTERACTION} FP64-pipe instructions per interaction over the measured DFMA issue rate",
+        "traffic": traffic if (world == 1 and n == (1 << 20)) else None,
+        "traffic_note": ("dram__bytes_read+write of one launch at N=2^20, ncu --set full (profiles/r2_sym_n1m.txt): almost all of it the "
+                         "RED.ADD.F64 updates of the per-CTA private accumulation arrays; " if pair_once else
+                         "dram__bytes_read+write of one launch at N=2^20, ncu --set full (profiles/r1_direct_sum_n1m_final.txt; includes the 28 MB of partial sums of split target blocks); ")
+                        + "algorithmic bytes = 32 B x N sources + 24 B x N results = 58.7 MB",
+        "kernel": ("direct_sum_sym_kernel (every unordered pair once, Newton-3 like the reference's i<j loop; + the finishing kernel, <0.3% of the stage)"
+                   if pair_once else "direct_sum_kernel<4,false,false> (+ the fix-up kernel of split target blocks, <0.1% of the stage)"),
+        "kernel_ms": k_ms, "path": path,
+        "convention": f"{FLOP_PER_INTERACTION} flop per ORDERED interaction, N(N-1) of them per force evaluation (SURVEY 8d), whatever the kernel really executes; "
+                      f"peak = {peak_src} (= {peak_mhz:.0f} MHz x 148 SM x 64 DFMA lanes x 2)",
+        "fp64_instr_per_ordered_interaction": ops,
+        "fp64_pipe_util": ops * k_inter / (k_ms * 1e-3) / (peak_tf * 1e12 / 2.0),
+        "fp64_pipe_util_note": f"{ops:g} FP64-pipe instructions really issued per ordered interaction over the measured DFMA issue rate: the honest "
+                               "utilisation figure; frac above uses the 20-flop convention and therefore credits the pair-once kernel for the half of the r^-3 work it does not repeat",
     }
 
     # end to end through the reference-facing call with host buffers
@@ -477,6 +490,29 @@ def run_b200_arm(args):
         a_all = ctx.accelerations()
         if rank == 0:
             parity = direct_sum_parity(x, m, G, args.eps, a_all)
+
+    # the same workload with unequal masses (the named Plummer sphere has equal masses, which lets the pair-once kernel
+    # factor the mass out: 9 instead of 10 FP64 instructions per ordered interaction)
+    gm = None
+    if not args.no_parity:
+        mg = m * np.random.default_rng(7).uniform(0.5, 1.5, n)
+        ctx.set_system(x, mg, G, v)
+        step(); ctx.synchronize()
+        g_ms = 0.0
+        kg = max(1, min(args.steps, 3))
+        barrier()
+        for _ in range(kg):
+            ctx.flush_l2()
+            ctx.event_record(0)
+            step()
+            ctx.event_record(1)
+            g_ms += ctx.event_elapsed_ms(0, 1)
+        g_ms = max_over_ranks(g_ms) / kg
+        gpath = ctx.direct_sum_path()
+        gm = {"value": inter / (g_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_ms, "steps": kg,
+              "workload": "same positions, masses drawn uniformly from [0.5, 1.5] / N",
+              "path": ("pair_once_equal_mass" if gpath[1] else "pair_once") if gpath[0] else "ordered"}
+        ctx.set_system(x, m, G, v)
 
     # Barnes-Hut (second half of the metric): s per full force evaluation, theta = 0.5, leaf = 1
     bh = None
@@ -573,19 +609,37 @@ def run_b200_arm(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"direct-sum pairwise FP64 force evaluation, {args.ic} N={n}, eps={args.eps}",
-                       "partition": f"targets sharded over {world} rank(s), NCCL all-gather of positions per step" if world > 1 else "single GPU",
+                       "partition": (f"pair units sharded evenly over {world} rank(s): NCCL all-gather of positions, all-reduce of the accelerations per step" if pair_once else
+                                     f"targets sharded over {world} rank(s), NCCL all-gather of positions per step") if world > 1 else "single GPU",
                        "l2": "256 MiB L2 flush between timed iterations",
                        # second half of BASELINE.json's metric ("... & BH force-eval s/step"): kept inside config so the
                        # driver's parser, which keeps config whole, carries it into BENCH / SCALE
                        "barnes_hut": bh},
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "massless": ml, "whfast": wh, "energy": en, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "unequal_masses": gm, "massless": ml, "whfast": wh, "energy": en, "gpu_launches": int(launches),
             "clocks": clocks, "allgather_ms": float(np.mean(gather_ms)) if world > 1 else 0.0,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sym_ncu_traffic():
+    """dram read + write bytes of one direct_sum_sym_kernel launch at N = 2^20 (profiles/r2_sym_n1m.txt), or None."""
+    try:
+        rd = wr = None
+        for ln in open(ROOT / "profiles" / "r2_sym_n1m.txt"):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                val = float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+                if f[0].endswith("read.sum") and rd is None:
+                    rd = val
+                if f[0].endswith("write.sum") and wr is None:
+                    wr = val
+        return int(rd + wr) if rd is not None and wr is not None else None
+    except Exception:
+        return None
 
 
 def _hbm_peak():

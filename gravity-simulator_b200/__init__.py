@@ -96,7 +96,8 @@ ABI_SYMBOLS = [
     "grav_b200_acceleration_massless", "grav_b200_acceleration_barnes_hut",
     "grav_b200_whfast_acceleration_pairwise", "grav_b200_whfast_acceleration_massless",
     "grav_b200_construct_octree", "grav_b200_morton_keys", "grav_b200_set_bh_mode", "grav_b200_get_bh_mode",
-    "grav_b200_set_bh_exact", "grav_b200_get_bh_exact", "grav_b200_ctx_create_team", "grav_b200_ctx_create_auto",
+    "grav_b200_set_bh_exact", "grav_b200_get_bh_exact", "grav_b200_set_direct_sum_mode", "grav_b200_get_direct_sum_mode",
+    "grav_b200_ctx_create_team", "grav_b200_ctx_create_auto",
     "grav_b200_ctx_team_size",
     "grav_b200_ctx_create", "grav_b200_ctx_destroy", "grav_b200_nccl_unique_id", "grav_b200_ctx_set_system",
     "grav_b200_ctx_set_positions", "grav_b200_ctx_num_particles", "grav_b200_ctx_owned_range",
@@ -104,7 +105,7 @@ ABI_SYMBOLS = [
     "grav_b200_ctx_get_accelerations", "grav_b200_ctx_leapfrog_begin", "grav_b200_ctx_leapfrog_steps", "grav_b200_ctx_leapfrog_end",
     "grav_b200_ctx_energy", "grav_b200_ctx_synchronize", "grav_b200_ctx_last_timing_ms",
     "grav_b200_kernel_launch_count", "grav_b200_measure_fp64_peak", "grav_b200_ctx_event_record",
-    "grav_b200_ctx_event_elapsed_ms", "grav_b200_ctx_flush_l2", "grav_b200_ctx_mark_positions_sharded",
+    "grav_b200_ctx_event_elapsed_ms", "grav_b200_ctx_flush_l2", "grav_b200_ctx_mark_positions_sharded", "grav_b200_ctx_direct_sum_path",
     "grav_b200_host_register", "grav_b200_host_unregister",
     "grav_b200_compute_energy", "grav_b200_ctx_fixed_begin", "grav_b200_ctx_fixed_steps", "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
 ]
@@ -166,6 +167,7 @@ def load():
     abi.grav_b200_ctx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     abi.grav_b200_ctx_flush_l2.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_mark_positions_sharded.argtypes = [C.c_void_p]
+    abi.grav_b200_ctx_direct_sum_path.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     abi.grav_b200_host_register.argtypes = [C.c_void_p, C.c_uint64]
     abi.grav_b200_host_unregister.argtypes = [C.c_void_p]
     abi.grav_b200_nccl_unique_id.argtypes = [C.c_void_p]
@@ -476,6 +478,12 @@ class Context:
 
     def mark_positions_sharded(self):
         check_rc(self.abi.grav_b200_ctx_mark_positions_sharded(self.h))
+
+    def direct_sum_path(self):
+        """(pair_once, equal_mass) of the last pairwise force evaluation."""
+        a, b = C.c_int(0), C.c_int(0)
+        check_rc(self.abi.grav_b200_ctx_direct_sum_path(self.h, C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
 
     def timing_ms(self, stage=0) -> float:
         ms = C.c_float()

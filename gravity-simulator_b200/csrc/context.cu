@@ -192,6 +192,21 @@ int grav_b200_set_bh_exact(int on)
     return GRAV_B200_OK;
 }
 
+static int g_ds_mode = -2;   // -2: not read from the environment yet
+int grav_b200_get_direct_sum_mode(void)
+{
+    if (g_ds_mode == -2) {
+        const char *e = getenv("GRAV_B200_DS_SYM");
+        g_ds_mode = e ? (atoi(e) > 0 ? 1 : (atoi(e) == 0 ? 0 : -1)) : -1;
+    }
+    return g_ds_mode;
+}
+int grav_b200_set_direct_sum_mode(int mode)
+{
+    g_ds_mode = mode > 0 ? 1 : (mode == 0 ? 0 : -1);
+    return GRAV_B200_OK;
+}
+
 int grav_b200_get_bh_exact(void)
 {
     if (g_bh_exact < 0) {
@@ -252,7 +267,7 @@ void grav_b200_ctx_destroy(grav_b200_ctx *c)
     whfast_state_free(c);
     comm_destroy(c);
     DevBuf *bufs[] = {&c->posm, &c->vel, &c->acc, &c->xcomp, &c->vcomp, &c->stage_a, &c->stage_b, &c->stage_c, &c->stage_d,
-                      &c->partials, &c->misc, &c->rk_buf, &c->msrc, &c->msrc_id, &c->msrc_altm, &c->l2_flush, &c->mflag, &c->mrank};
+                      &c->partials, &c->sym_priv, &c->sym_flag, &c->misc, &c->rk_buf, &c->msrc, &c->msrc_id, &c->msrc_altm, &c->l2_flush, &c->mflag, &c->mrank};
     for (DevBuf *b : bufs) b->release();
     DevTree &t = c->tree;
     DevBuf *tb[] = {&t.keys_unsorted, &t.keys, &t.perm, &t.keys_tmp, &t.perm_tmp, &t.hist, &t.bbox, &t.exp_rec,
@@ -456,6 +471,21 @@ int grav_b200_ctx_event_elapsed_ms(grav_b200_ctx *c, int a, int b, float *ms)
     GB_CUDA(cudaSetDevice(c->device));
     GB_CUDA(cudaEventSynchronize(c->user_ev[b]));
     GB_CUDA(cudaEventElapsedTime(ms, c->user_ev[a], c->user_ev[b]));
+    return GRAV_B200_OK;
+}
+
+int grav_b200_ctx_direct_sum_path(grav_b200_ctx *c, int *pair_once, int *equal_mass)
+{
+    if (!c || !pair_once || !equal_mass) { set_error("NULL pointer"); return GRAV_B200_EINVAL; }
+    GB_CUDA(cudaSetDevice(c->device));
+    *pair_once = c->last_ds_sym;
+    *equal_mass = 0;
+    if (c->last_ds_sym && c->sym_flag.p) {
+        int flag = 0;
+        GB_CUDA(cudaMemcpyAsync(&flag, c->sym_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        *equal_mass = flag != 0;
+    }
     return GRAV_B200_OK;
 }
 

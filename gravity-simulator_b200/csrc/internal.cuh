@@ -161,6 +161,10 @@ struct grav_b200_ctx {
     gb::DevBuf xcomp, vcomp;      // compensated-summation error terms, double[3n]
     gb::DevBuf stage_a, stage_b, stage_c, stage_d;  // H2D/D2H staging
     gb::DevBuf partials;  // direct-sum split-segment partial sums
+    gb::DevBuf sym_priv;  // pair-once direct sum: one private accumulation array per CTA (direct_sum_sym.cu), all zero between calls
+    gb::DevBuf sym_flag;  // pair-once direct sum: equal-mass flag + the common mass
+    bool sym_priv_clean = false, sym_attr_set = false;
+    int last_ds_sym = 0;  // the last pairwise force evaluation took the pair-once path
     gb::DevBuf misc;      // small scratch (reductions)
     // massless method scratch
     gb::DevBuf msrc, msrc_id, msrc_altm, mflag, mrank;
@@ -195,6 +199,9 @@ namespace gb {
 // direct_sum.cu
 int direct_sum_pairwise(grav_b200_ctx *c, double eps);
 int direct_sum_massless(grav_b200_ctx *c, double eps);
+// direct_sum_sym.cu
+bool direct_sum_sym_wanted(const grav_b200_ctx *c);
+int direct_sum_pairwise_sym(grav_b200_ctx *c, double eps);
 int direct_sum_small_host(grav_b200_ctx *c, double *a, int n, const double *x, const double *m, double G, double eps);
 // small_mailbox.cu
 int mailbox_pairwise(grav_b200_ctx *c, double *a, int n, const double *x, const double *m, double G, double eps);

@@ -130,6 +130,16 @@ int grav_b200_get_bh_mode(void);
 int grav_b200_set_bh_exact(int on);
 int grav_b200_get_bh_exact(void);
 
+/* How the pairwise direct sum (src/acceleration.c:177-234) is evaluated.
+ *   -1 (default)  automatic: systems large enough to balance evaluate every unordered pair ONCE and apply it to both
+ *                 particles, like the reference's i < j loop (10 FP64 instructions per ordered interaction, 9 with equal
+ *                 masses); smaller ones evaluate every ordered interaction (16 instructions, finer work units)
+ *    0            ordered interactions always
+ *    1            pair-once whenever the system has at least 256 particles
+ * Both agree with the reference to <= 1e-12 relative.  Also settable with GRAV_B200_DS_SYM (read once). */
+int grav_b200_set_direct_sum_mode(int mode);
+int grav_b200_get_direct_sum_mode(void);
+
 /* ---- (2) device-resident context ---------------------------------------------------- */
 
 typedef struct grav_b200_ctx grav_b200_ctx;
@@ -244,6 +254,10 @@ int grav_b200_ctx_event_record(grav_b200_ctx *ctx, int slot);
 int grav_b200_ctx_event_elapsed_ms(grav_b200_ctx *ctx, int slot_a, int slot_b, float *ms);
 int grav_b200_ctx_flush_l2(grav_b200_ctx *ctx);
 int grav_b200_ctx_mark_positions_sharded(grav_b200_ctx *ctx);
+/* Which formulation the context's last pairwise force evaluation used (measurement / reporting only):
+ * *pair_once = 1 for the pair-once kernel, 0 for ordered interactions; *equal_mass = 1 when that evaluation found all
+ * masses equal and factored the mass out.  Synchronises the context's stream. */
+int grav_b200_ctx_direct_sum_path(grav_b200_ctx *ctx, int *pair_once, int *equal_mass);
 int grav_b200_host_register(void *ptr, uint64_t bytes);
 int grav_b200_host_unregister(void *ptr);
 /* Number of kernels this library launched since process start (all contexts). */

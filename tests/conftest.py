@@ -99,3 +99,21 @@ class bh_exact:
 
     def __exit__(self, *exc):
         self.abi.grav_b200_set_bh_exact(self.prev)
+
+
+class ds_mode:
+    """with ds_mode(gb, 1): ...   -- formulation of the pairwise direct sum (include/grav_b200.h,
+    grav_b200_set_direct_sum_mode): 1 = every unordered pair once wherever the system has two rows, 0 = ordered
+    interactions always, -1 = automatic (default)."""
+
+    def __init__(self, gb, mode):
+        self.abi, _ = gb.load()
+        self.mode = int(mode)
+
+    def __enter__(self):
+        self.prev = int(self.abi.grav_b200_get_direct_sum_mode())
+        self.abi.grav_b200_set_direct_sum_mode(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        self.abi.grav_b200_set_direct_sum_mode(self.prev)

@@ -40,15 +40,22 @@ def main():
         single.set_system(x, m, G, v); multi.set_system(x, m, G, v)
         lo, hi = multi.owned_range()
         check(f"n={n}: owned range [{lo},{hi}) matches rank*n/world", lo == rank * n // world and hi == (rank + 1) * n // world)
-        for method, kw in (("pairwise", dict(softening_length=0.01)), ("barnes_hut", dict(softening_length=0.01, opening_angle=0.5)),
-                           ("massless", dict(softening_length=0.0))):
+        abi, _ = gb.load()
+        # pairwise in both formulations (include/grav_b200.h, grav_b200_set_direct_sum_mode): ordered interactions with the
+        # targets sharded, and every pair once with the pair units sharded and an all-reduce of the accelerations
+        for method, kw, ds in (("pairwise", dict(softening_length=0.01), -1), ("pairwise", dict(softening_length=0.01), 0),
+                               ("pairwise", dict(softening_length=0.01), 1), ("barnes_hut", dict(softening_length=0.01, opening_angle=0.5), -1),
+                               ("massless", dict(softening_length=0.0), -1)):
+            abi.grav_b200_set_direct_sum_mode(ds)
             single.acceleration(method, **kw); multi.mark_positions_sharded(); multi.acceleration(method, **kw)
             a1, aN = single.accelerations(), multi.accelerations()
+            abi.grav_b200_set_direct_sum_mode(-1)
             if method == "barnes_hut":   # per-target serial arithmetic: independent of the partition
                 check(f"n={n} {method}: sharded over {world} ranks == single GPU (bit-exact)", np.array_equal(a1, aN, equal_nan=True))
-            else:                        # the stream-K split points move with the shard, so only rounding differs
+            else:                        # the split points of the work move with the shard, so only rounding differs
                 err = float(np.max(np.linalg.norm(a1 - aN, axis=1) / np.linalg.norm(a1, axis=1)))
-                check(f"n={n} {method}: sharded over {world} ranks vs single GPU max rel {err:.1e} <= 1e-13", err <= 1e-13)
+                path = {-1: "auto", 0: "ordered", 1: "pair-once"}[ds] + (f" -> pair-once {multi.direct_sum_path()}" if method == "pairwise" else "")
+                check(f"n={n} {method} [{path}]: sharded over {world} ranks vs single GPU max rel {err:.1e} <= 3e-13", err <= 3e-13)
         dt = 1e-3
         for c in (single, multi):
             c.set_system(x, m, G, v)

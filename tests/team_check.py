@@ -1,7 +1,7 @@
 """In-process device team check (needs >= 2 GPUs):  python tests/team_check.py [k]
 
 (1) grav_b200_ctx_create_team: the sharded direct sum / massless / Barnes-Hut / leapfrog / RK4 / energy driven from ONE
-    thread against the single-GPU results (direct sums <= 1e-13, Barnes-Hut bit-equal: every target is walked by one warp
+    thread against the single-GPU results (direct sums <= 3e-13, Barnes-Hut bit-equal: every target is walked by one warp
     in the same way whichever rank owns it).
 (2) GRAV_B200_DEVICES=k behind the reference's own entry points: acceleration() and launch_simulation_python of the
     drop-in build (config 2- and config 4-shaped problems at N = 2^18) in fresh processes, one with k devices and one with
@@ -81,7 +81,7 @@ def main():
                 check(f"n={n} {method}: team == single GPU (bit-exact)", np.array_equal(a1, aN, equal_nan=True))
             else:
                 e = rel(aN, a1)
-                check(f"n={n} {method}: team vs single GPU max rel {e:.1e} <= 1e-13", e <= 1e-13)
+                check(f"n={n} {method}: team vs single GPU max rel {e:.1e} <= 3e-13", e <= 3e-13)
         if n > 100000:
             continue
         dt = 1e-3
@@ -116,7 +116,7 @@ def main():
             outs[tag] = dict(np.load(out)) if r.returncode == 0 else {}
         s, t = outs["single"], outs["team"]
         if s and t:
-            check(f"acceleration() pairwise N=2^18 on {k} GPUs vs 1: {rel(t['a_pairwise'], s['a_pairwise']):.1e} <= 1e-13", rel(t["a_pairwise"], s["a_pairwise"]) <= 1e-13)
+            check(f"acceleration() pairwise N=2^18 on {k} GPUs vs 1: {rel(t['a_pairwise'], s['a_pairwise']):.1e} <= 3e-13", rel(t["a_pairwise"], s["a_pairwise"]) <= 3e-13)
             check(f"acceleration() massless N=50009 on {k} GPUs vs 1: {rel(t['a_massless'], s['a_massless']):.1e} <= 1e-13", rel(t["a_massless"], s["a_massless"]) <= 1e-13)
             check(f"acceleration() barnes_hut N=2^18 on {k} GPUs == 1 GPU (bit-exact)", np.array_equal(t["a_bh"], s["a_bh"]))
             if "lf_bh_x" in s:

@@ -2,12 +2,13 @@
 the golden vectors of the unmodified reference and against the CPU oracle on fresh seeded inputs.
 
 Tolerance (BASELINE.json north_star / SURVEY.md section 8d): max_i |a_gpu - a_ref|_2 / |a_ref|_2 <= 1e-12.
-The GPU evaluates every ordered interaction row-wise with FMA; the reference walks unordered pairs with
-Newton-3 updates, so only the summation order and rounding differ."""
+Two GPU formulations (include/grav_b200.h, grav_b200_set_direct_sum_mode): every ordered interaction row-wise
+(direct_sum.cu; small systems) and every unordered pair once with Newton-3 updates like the reference's own loop
+(direct_sum_sym.cu; N >= 16384 on one GPU).  Against the reference only the summation order and rounding differ."""
 import numpy as np
 import pytest
 
-from conftest import max_rel_err
+from conftest import assert_forces_close, ds_mode, max_rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -119,3 +120,73 @@ def test_context_resident_matches_one_shot(gb, ics):
         a = c.accelerations()
         assert np.array_equal(c.positions(), x)
     assert np.array_equal(a, gb.acceleration(x, m, G, "pairwise", 0.0))
+
+
+# ---- pair-once formulation (direct_sum_sym.cu), forced for every size that has two rows of 256 particles ---------------
+
+@pytest.mark.parametrize("masses", ["equal", "unequal", "some zero"])
+@pytest.mark.parametrize("n,eps", [(512, 0.01), (513, 0.0), (777, 0.0), (1000, 0.01), (2049, 0.0), (4099, 0.02), (8192, 0.0),
+                                   (16384, 0.01), (40001, 0.0)])
+def test_pair_once_vs_oracle_sizes(gb, oracle, ics, n, eps, masses):
+    """Ragged sizes around the row (256) and group (32) boundaries, with and without softening; equal masses take the
+    factored-mass loop, unequal ones the general loop.  eps = 0 runs put a real particle on the origin, where the zero
+    padding of the particle buffer sits (the masked loop of the last group)."""
+    x, v, m, G = ics.plummer(n, seed=n)
+    rng = np.random.default_rng(n)
+    if masses != "equal":
+        m = m * rng.uniform(0.5, 1.5, n)
+    if masses == "some zero":
+        m[rng.random(n) < 0.3] = 0.0
+    if eps == 0.0:
+        x[n // 3] = 0.0
+    with ds_mode(gb, 1):
+        with gb.Context() as c:
+            c.set_system(x, m, G, v)
+            c.acceleration("pairwise", eps)
+            a = c.accelerations()
+            assert c.direct_sum_path() == (True, masses == "equal")
+            c.acceleration("pairwise", eps)       # the private accumulation arrays were left zeroed: same bits again
+            assert np.array_equal(a, c.accelerations())
+    ref = oracle.acceleration(x, m, G, "pairwise", eps) if n <= 16384 else None
+    if ref is None:
+        tg = rng.choice(n, 256, replace=False).astype(np.int32)
+        assert max_rel_err(a[tg], oracle.pairwise_targets(x, m, G, eps, tg)) <= TOL
+    else:
+        assert max_rel_err(a, ref) <= TOL
+
+
+@pytest.mark.parametrize("case", ["plummer2048", "uniform1500", "clustered1024"])
+def test_pair_once_matches_golden(gb, golden, case):
+    g = golden(case)
+    with ds_mode(gb, 1):
+        a = gb.acceleration(g["x"], g["m"], float(g["G"]), "pairwise", float(g["eps"]))
+    assert_forces_close(a, g["a_pairwise"], TOL, case)
+
+
+def test_pair_once_coincident_particles(gb, oracle):
+    """The NaN pattern of the reference (both members of a coincident pair, nobody else), also across rows / groups."""
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(1500, 3)); x[17] = x[400]; x[1499] = x[1200]
+    m = rng.random(1500) + 0.1
+    with ds_mode(gb, 1):
+        a = gb.acceleration(x, m, 1.0, "pairwise", 0.0)
+    assert_forces_close(a, oracle.acceleration(x, m, 1.0, "pairwise", 0.0), TOL)
+    assert sorted(np.flatnonzero(np.isnan(a).any(axis=1))) == [17, 400, 1200, 1499]
+
+
+def test_formulations_agree_at_size(gb, ics):
+    """N = 2^17: ordered interactions vs pair-once (equal and unequal masses) agree to the parity tolerance, the automatic
+    choice is pair-once, and the mass scaling is exact in the factored-mass loop."""
+    n = 1 << 17
+    x, v, m, G = ics.plummer(n, seed=33)
+    for mm in (m, m * np.random.default_rng(2).uniform(0.2, 3.0, n)):
+        with ds_mode(gb, 0):
+            a0 = gb.acceleration(x, mm, G, "pairwise", 0.01)
+        with ds_mode(gb, 1):
+            a1 = gb.acceleration(x, mm, G, "pairwise", 0.01)
+        assert max_rel_err(a1, a0) <= TOL
+        with gb.Context() as c:
+            c.set_system(x, mm, G, v)
+            c.acceleration("pairwise", 0.01)
+            assert c.direct_sum_path()[0]
+            assert np.array_equal(c.accelerations(), a1)

@@ -4,7 +4,7 @@ the accelerations of the exact walk; the default cooperative walk and the direct
 import numpy as np
 import pytest
 
-from conftest import bh_exact, max_rel_err
+from conftest import bh_exact, ds_mode, max_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -50,9 +50,15 @@ def test_fuzz_all_methods(gb, oracle, seed):
     assert np.array_equal(a, ao, equal_nan=True), (seed, "bh", max_rel_err(np.nan_to_num(a), np.nan_to_num(ao)))
     # cooperative Barnes-Hut walk and direct sums: 1e-12 on every particle where the reference is finite and non-zero;
     # NaN/inf pattern identical
-    for method in ("barnes_hut", "pairwise", "massless"):
+    for method in ("barnes_hut", "pairwise", "pairwise, every pair once", "massless"):
         if method == "barnes_hut":
             a = gb.acceleration(x, m, G, method, eps, theta, leaf)
+        elif method == "pairwise, every pair once":
+            if x.shape[0] < 512:
+                continue
+            with ds_mode(gb, 1):
+                a = gb.acceleration(x, m, G, "pairwise", eps)
+            ao = oracle.acceleration(x, m, G, "pairwise", eps)
         else:
             a = gb.acceleration(x, m, G, method, eps)
             ao = oracle.acceleration(x, m, G, method, eps)

@@ -285,12 +285,40 @@ __global__ void __launch_bounds__(SY_ROW) direct_sum_sym_finish_kernel(const Sym
     }
     __syncthreads();
     const int cmax = s_cmax;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int c = 0; inb && c <= cmax; c++) {
-        double *P = p.priv + (size_t)c * p.stride + 3 * (size_t)i;
-        sx += P[0]; sy += P[1]; sz += P[2];
-        P[0] = 0.0; P[1] = 0.0; P[2] = 0.0;
+    // the block's 3 * SY_ROW sums as flat, fully coalesced columns (thread t takes elements t, t + SY_ROW, t + 2 SY_ROW of
+    // every contributing array, four arrays in flight), then regrouped per particle through shared memory
+    __shared__ double s_sum[3 * SY_ROW];
+    {
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+        const size_t e0 = 3 * (size_t)b * SY_ROW + tid;
+        const bool in0 = (long long)(e0) < p.stride, in1 = (long long)(e0 + SY_ROW) < p.stride, in2 = (long long)(e0 + 2 * SY_ROW) < p.stride;
+        int c = 0;
+        for (; c + 4 <= cmax + 1; c += 4) {
+            double v[4][3];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double *P = p.priv + (size_t)(c + q) * p.stride + e0;
+                v[q][0] = in0 ? P[0] : 0.0; v[q][1] = in1 ? P[SY_ROW] : 0.0; v[q][2] = in2 ? P[2 * SY_ROW] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double *P = p.priv + (size_t)(c + q) * p.stride + e0;
+                f0 += v[q][0]; f1 += v[q][1]; f2 += v[q][2];
+                if (in0) P[0] = 0.0;
+                if (in1) P[SY_ROW] = 0.0;
+                if (in2) P[2 * SY_ROW] = 0.0;
+            }
+        }
+        for (; c <= cmax; c++) {
+            double *P = p.priv + (size_t)c * p.stride + e0;
+            if (in0) { f0 += P[0]; P[0] = 0.0; }
+            if (in1) { f1 += P[SY_ROW]; P[SY_ROW] = 0.0; }
+            if (in2) { f2 += P[2 * SY_ROW]; P[2 * SY_ROW] = 0.0; }
+        }
+        s_sum[tid] = f0; s_sum[tid + SY_ROW] = f1; s_sum[tid + 2 * SY_ROW] = f2;
     }
+    __syncthreads();
+    double sx = s_sum[3 * tid + 0], sy = s_sum[3 * tid + 1], sz = s_sum[3 * tid + 2];
     const bool eqm = (*p.eqm_flag != 0);
     if (eqm) {
         const double m0 = *p.eqm_mass;

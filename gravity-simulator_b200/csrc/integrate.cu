@@ -200,25 +200,25 @@ int synced_velocities(grav_b200_ctx *c, double **d_out)
 // Same tile machinery as the direct sum (direct_sum.cu): TI targets per thread in registers, sources streamed through a
 // shared-memory tile, and m_j / r_ij from the MUFU.RSQ64H seed y0 (|e| <~ 2^-20, e = 1 - r2 y0^2) with one correction,
 // r2^-1/2 = y0 (1 + e (1/2 + 3/8 e)) -- the dropped term 5/16 e^3 is < 2^-61 -- i.e. 13 FP64-pipe instructions per
-// ordered pair instead of the ~45 of sqrt + division.  Every thread sums m_j / r_ij over all j != i for its targets, so the
-// pair sum is G/2 sum_i m_i pot_i; block partial sums are written out and added in block order by one thread:
-// deterministic.  Coincident particles give a non-finite energy like the reference's 1/0.
+// pair instead of the ~45 of sqrt + division.  Every unordered pair is visited ONCE, like the reference's i < j loop: a
+// target sums m_j / r_ij over the sources j > i only, so a block of targets streams the tiles from its own onwards.  To
+// keep the CTAs equally loaded a CTA takes target block q and its mirror image NB - 1 - q (together NT + 1 tiles whatever
+// q is), and the ranks of a multi-GPU run take the q in turn.  The kinetic term is summed over the rank's own targets
+// (velocities are sharded).  Block partial sums are written out and added in block order by one thread: deterministic.
+// Coincident particles give a non-finite energy like the reference's 1/0.
 template <int TI>
-__global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__ posm, const double *__restrict__ v, int n, int n_pad,
-                                                    int lo, int hi, double G, double *__restrict__ block_out)
+__device__ __forceinline__ double energy_block_potential(const double4 *__restrict__ posm, int n, int n_pad, int blk, double4 *tile)
 {
-    __shared__ double4 tile[256];
-    __shared__ double red[256];
     double xi[TI], yi[TI], zi[TI], mi[TI], pot[TI];
     int ii[TI];
 #pragma unroll
     for (int t = 0; t < TI; t++) {
-        ii[t] = lo + (blockIdx.x * TI + t) * 256 + threadIdx.x;
-        const double4 me = (ii[t] < hi) ? posm[ii[t]] : make_double4(0.0, 0.0, 0.0, 0.0);
+        ii[t] = (blk * TI + t) * 256 + threadIdx.x;
+        const double4 me = (ii[t] < n) ? posm[ii[t]] : make_double4(0.0, 0.0, 0.0, 0.0);
         xi[t] = me.x; yi[t] = me.y; zi[t] = me.z; mi[t] = me.w;
         pot[t] = 0.0;
     }
-    for (int j0 = 0; j0 < n_pad; j0 += 256) {
+    for (int j0 = blk * TI * 256; j0 < n_pad; j0 += 256) {
         __syncthreads();
         tile[threadIdx.x] = posm[j0 + threadIdx.x];
         __syncthreads();
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__
                 const double e = fma(-r2, y * y, 1.0);
                 const double my = q.w * y;
                 double w = fma(my, e * fma(0.375, e, 0.5), my);     // m_j / r
-                if (j0 + j == ii[t]) w = 0.0;                         // the self term only
+                if (j0 + j <= ii[t]) w = 0.0;                         // only the partners behind the target (and not itself)
                 pot[t] += w;
             }
         }
@@ -242,22 +242,40 @@ __global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__
     double e = 0.0;
 #pragma unroll
     for (int t = 0; t < TI; t++) {
-        if (ii[t] < hi && pot[t] != pot[t]) {
+        if (ii[t] < n && pot[t] != pot[t]) {
             // r = 0 (another particle at the same point) turns the seed into inf and the correction into NaN; the reference
             // divides by zero there (m / 0 = inf, or NaN for a massless partner): repeat this one target with the division
             double p = 0.0;
-            for (int j = 0; j < n; j++) {
-                if (j == ii[t]) continue;
+            for (int j = ii[t] + 1; j < n; j++) {
                 const double4 q = posm[j];
                 const double dx = q.x - xi[t], dy = q.y - yi[t], dz = q.z - zi[t];
                 p += q.w / sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
             }
             pot[t] = p;
         }
-        if (ii[t] < hi) {
-            const double vx = v[3 * (size_t)ii[t]], vy = v[3 * (size_t)ii[t] + 1], vz = v[3 * (size_t)ii[t] + 2];
-            e += 0.5 * mi[t] * (vx * vx + vy * vy + vz * vz) - 0.5 * G * mi[t] * pot[t];
-        }
+        if (ii[t] < n) e -= mi[t] * pot[t];
+    }
+    return e;      // - sum over the block's targets of m_i sum_{j>i} m_j / r_ij   (G applied by the caller)
+}
+
+template <int TI>
+__global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__ posm, const double *__restrict__ v, int n, int n_pad,
+                                                    int lo, int hi, int rank, int world, double G, double *__restrict__ block_out)
+{
+    __shared__ double4 tile[256];
+    __shared__ double red[256];
+    const int NB = (n + 256 * TI - 1) / (256 * TI);
+    const int q = blockIdx.x * world + rank;           // this CTA's target block and, mirrored, its partner
+    double e = 0.0;
+    if (q < (NB + 1) / 2) {
+        e = energy_block_potential<TI>(posm, n, n_pad, q, tile);
+        if (NB - 1 - q != q) e += energy_block_potential<TI>(posm, n, n_pad, NB - 1 - q, tile);
+        e *= G;
+    }
+    // kinetic energy of the rank's own targets, spread over the CTAs
+    for (int i = lo + blockIdx.x * 256 + threadIdx.x; i < hi; i += gridDim.x * 256) {
+        const double vx = v[3 * (size_t)i], vy = v[3 * (size_t)i + 1], vz = v[3 * (size_t)i + 2];
+        e += 0.5 * posm[i].w * (vx * vx + vy * vy + vz * vz);
     }
     red[threadIdx.x] = e;
     __syncthreads();
@@ -420,15 +438,16 @@ int grav_b200_ctx_energy(grav_b200_ctx *c, double *energy)
     if (c->world > 1 && !c->posm_gathered) { GB_TRY(comm_allgather_posm(c)); c->posm_gathered = true; }
     double *d_v;
     GB_TRY(synced_velocities(c, &d_v));
-    const int cnt = c->hi - c->lo;
-    // four targets per thread once that still leaves two CTAs per SM; one target per thread below (small systems need the CTAs)
-    const bool ti4 = (cnt + 1023) / 1024 >= 2 * c->sm_count;
-    const int blocks = ti4 ? (cnt + 1023) / 1024 : (cnt + 255) / 256;
+    // every unordered pair once: a CTA takes a block of targets and its mirror image, the ranks take the CTAs in turn.
+    // Four targets per thread once that still leaves two CTAs per SM; one target per thread below (small systems need the CTAs)
+    auto ctas_for = [&](int ti) { const int nb = (c->n + 256 * ti - 1) / (256 * ti); const int pairs = (nb + 1) / 2; return (pairs + c->world - 1) / c->world; };
+    const bool ti4 = ctas_for(4) >= 2 * c->sm_count;
+    const int blocks = ti4 ? ctas_for(4) : ctas_for(1);
     GB_TRY(c->misc.reserve(sizeof(double) * ((size_t)blocks + 2)));
     double *part = c->misc.as<double>();
     if (blocks > 0) {
-        if (ti4) energy_kernel<4><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->G, part + 1);
-        else energy_kernel<1><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->G, part + 1);
+        if (ti4) energy_kernel<4><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->rank, c->world, c->G, part + 1);
+        else energy_kernel<1><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->rank, c->world, c->G, part + 1);
         GB_LAUNCH_CHECK();
         count_launch();
     }

@@ -54,7 +54,10 @@ def main():
                 check(f"n={n} {method}: sharded over {world} ranks == single GPU (bit-exact)", np.array_equal(a1, aN, equal_nan=True))
             else:                        # the split points of the work move with the shard, so only rounding differs
                 err = float(np.max(np.linalg.norm(a1 - aN, axis=1) / np.linalg.norm(a1, axis=1)))
-                path = {-1: "auto", 0: "ordered", 1: "pair-once"}[ds] + (f" -> pair-once {multi.direct_sum_path()}" if method == "pairwise" else "")
+                path = {-1: "auto", 0: "forced ordered", 1: "forced pair-once"}[ds]
+                if method == "pairwise":
+                    po, eq = multi.direct_sum_path()
+                    path += ": " + (("pair-once, equal masses" if eq else "pair-once") if po else "ordered interactions")
                 check(f"n={n} {method} [{path}]: sharded over {world} ranks vs single GPU max rel {err:.1e} <= 3e-13", err <= 3e-13)
         dt = 1e-3
         for c in (single, multi):

@@ -310,6 +310,7 @@ static int set_system_impl(grav_b200_ctx *c, int n, const double *x, const doubl
     c->lf_ready = false;
     c->fixed_integrator = 0;
     c->mlist_valid = false;
+    c->sym_eqm_valid = false;
     const size_t b3 = sizeof(double) * 3 * (size_t)n;
     GB_TRY(c->posm.reserve(sizeof(double4) * (size_t)c->n_pad));
     GB_TRY(c->acc.reserve(b3));

@@ -261,30 +261,42 @@ __global__ void __launch_bounds__(SY_THREADS, 1) direct_sum_sym_kernel(const Sym
     }
 }
 
+// Whether CTA cg of the decomposition added anything to the entries of block b (particles [b SY_ROW, (b+1) SY_ROW)): as one
+// of its rows (i-side) or inside the group ranges it met (j-side).  May say yes for a CTA that did not (reading zeros is
+// harmless); never says no for one that did -- the finishing kernel leaves exactly the touched entries zeroed.
+__device__ inline bool sym_cta_touches(const SymArgs &p, long long cg, int b)
+{
+    const long long u0 = sym_unit_begin(cg, p.U, p.ctas_total), u1 = sym_unit_begin(cg + 1, p.U, p.ctas_total);
+    if (u0 >= u1) return false;
+    const int A0 = sym_row_of(u0, p.NG, p.NR), A1 = sym_row_of(u1 - 1, p.NG, p.NR);
+    if (b < A0) return false;
+    if (b <= A1) return true;                     // one of its rows
+    if (A1 - A0 >= 2) return true;                // row A0 + 1 is covered completely and lies before b
+    // group range of block b in the k-coordinate of row A:  [SY_GPR (b - A - 1), SY_GPR (b - A - 1) + SY_GPR)
+    const long long ka0 = u0 - sym_row_start(A0, p.NG);
+    const long long kend0 = (A1 > A0) ? (long long)(p.NG - SY_GPR * (A0 + 1)) : (u1 - sym_row_start(A0, p.NG));
+    const long long kb_lo0 = (long long)SY_GPR * (b - A0 - 1);
+    if (kb_lo0 < kend0 && kb_lo0 + SY_GPR > ka0) return true;
+    if (A1 > A0) {
+        const long long kend1 = u1 - sym_row_start(A1, p.NG);
+        if ((long long)SY_GPR * (b - A1 - 1) < kend1) return true;
+    }
+    return false;
+}
+
 // acc[i] = G * (sum of the private arrays that can hold something for i, in CTA order, + the pairs inside i's own
 // block of SY_ROW particles); the private entries are zeroed on the way.  One thread per particle, one CTA per block.
 __global__ void __launch_bounds__(SY_ROW) direct_sum_sym_finish_kernel(const SymArgs p, int ctas_local)
 {
     __shared__ double4 blk[SY_ROW];
-    __shared__ int s_cmax;
+    __shared__ unsigned char s_touch[1024];          // per local CTA: did it add anything to this block's entries?
     const int b = blockIdx.x, tid = threadIdx.x;
     const int i = b * SY_ROW + tid;
     const bool inb = 3 * (long long)i < p.stride;      // inside the padded arrays
     blk[tid] = inb ? p.posm[i] : make_double4(0.0, 0.0, 0.0, 0.0);
-    if (tid == 0) {
-        // CTA c touches rows >= A0(c) and j-particles beyond row A0(c), i.e. nothing below particle SY_ROW * A0(c); A0 does
-        // not decrease with c, so the contributors of block b are a prefix of the CTAs
-        int lo = -1, hi = ctas_local - 1;     // largest c with A0(c) <= b (c with an empty range count as contributors of nothing)
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            const long long ub = sym_unit_begin((long long)p.cta0 + mid, p.U, p.ctas_total);
-            const int A0 = (p.U > 0 && ub < p.U) ? sym_row_of(ub, p.NG, p.NR) : p.NR;
-            if (A0 <= b) lo = mid; else hi = mid - 1;
-        }
-        s_cmax = lo;
-    }
+    for (int c = tid; c < ctas_local; c += SY_ROW) s_touch[c] = sym_cta_touches(p, (long long)p.cta0 + c, b) ? 1 : 0;
     __syncthreads();
-    const int cmax = s_cmax;
+    const int cmax = ctas_local - 1;
     // the block's 3 * SY_ROW sums as flat, fully coalesced columns (thread t takes elements t, t + SY_ROW, t + 2 SY_ROW of
     // every contributing array, four arrays in flight), then regrouped per particle through shared memory
     __shared__ double s_sum[3 * SY_ROW];
@@ -295,14 +307,17 @@ __global__ void __launch_bounds__(SY_ROW) direct_sum_sym_finish_kernel(const Sym
         int c = 0;
         for (; c + 4 <= cmax + 1; c += 4) {
             double v[4][3];
+            bool tc[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 double *P = p.priv + (size_t)(c + q) * p.stride + e0;
-                v[q][0] = in0 ? P[0] : 0.0; v[q][1] = in1 ? P[SY_ROW] : 0.0; v[q][2] = in2 ? P[2 * SY_ROW] : 0.0;
+                tc[q] = s_touch[c + q] != 0;
+                v[q][0] = (tc[q] && in0) ? P[0] : 0.0; v[q][1] = (tc[q] && in1) ? P[SY_ROW] : 0.0; v[q][2] = (tc[q] && in2) ? P[2 * SY_ROW] : 0.0;
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 double *P = p.priv + (size_t)(c + q) * p.stride + e0;
+                if (!tc[q]) continue;              // adding its zeros would not change a bit (x + 0.0 = x; the sums start at +0.0)
                 f0 += v[q][0]; f1 += v[q][1]; f2 += v[q][2];
                 if (in0) P[0] = 0.0;
                 if (in1) P[SY_ROW] = 0.0;
@@ -310,6 +325,7 @@ __global__ void __launch_bounds__(SY_ROW) direct_sum_sym_finish_kernel(const Sym
             }
         }
         for (; c <= cmax; c++) {
+            if (!s_touch[c]) continue;
             double *P = p.priv + (size_t)c * p.stride + e0;
             if (in0) { f0 += P[0]; P[0] = 0.0; }
             if (in1) { f1 += P[SY_ROW]; P[SY_ROW] = 0.0; }
@@ -378,7 +394,10 @@ bool direct_sum_sym_wanted(const grav_b200_ctx *c)
     static const long long budget_gb = getenv("GRAV_B200_DS_SYM_MAX_GB") ? atoll(getenv("GRAV_B200_DS_SYM_MAX_GB")) : 40;
     if (bytes > (size_t)budget_gb << 30) return false;
     if (mode == 1) return U >= 1;
-    static const long long min_units = getenv("GRAV_B200_DS_SYM_MIN_UNITS") ? atoll(getenv("GRAV_B200_DS_SYM_MIN_UNITS")) : 100;
+    // measured crossover on one GPU (profiles/r2_sym_variants.txt): a tie at N = 8192 (27 units per CTA), +25 % at 12288 (61);
+    // with several ranks the all-reduce of the results has to be paid for too
+    static const long long min_units = getenv("GRAV_B200_DS_SYM_MIN_UNITS") ? atoll(getenv("GRAV_B200_DS_SYM_MIN_UNITS")) : 40;
+    if (c->world > 1) return U >= 2 * min_units * ctas;
     return U >= min_units * ctas;
 }
 
@@ -390,33 +409,43 @@ int direct_sum_pairwise_sym(grav_b200_ctx *c, double eps)
     a.NR = (c->n + SY_ROW - 1) / SY_ROW;
     a.NG = (c->n + 31) / 32;
     a.U = sym_row_start(a.NR - 1, a.NG);
-    const int ctas = c->sm_count;
+    const int ctas = c->sm_count < 1024 ? c->sm_count : 1024;     // one per SM (the finishing kernel's contributor table holds 1024)
     a.cta0 = c->rank * ctas;
     a.ctas_total = c->world * ctas;
+    a.diag_rank = c->rank;
+    a.diag_world = c->world;
+    // measurement hook: the share of rank 0 of a k-rank run on one GPU (results are partial sums then)
+    static const int fake_world = getenv("GRAV_B200_DS_SYM_FAKE_WORLD") ? atoi(getenv("GRAV_B200_DS_SYM_FAKE_WORLD")) : 0;
+    if (fake_world > 1 && c->world == 1) { a.ctas_total = fake_world * ctas; a.diag_world = fake_world; }
     a.eps2 = eps * eps;
     a.G = c->G;
     a.stride = 3 * (long long)c->n_pad;
     a.acc = c->acc.as<double>();
-    a.diag_rank = c->rank;
-    a.diag_world = c->world;
     const size_t bytes = (size_t)ctas * (size_t)a.stride * sizeof(double);
-    if (c->sym_priv.cap < bytes || !c->sym_priv_clean) {
+    // the arrays are all zero between calls as long as every call finishes (and zeroes) what it touched; a different
+    // system size or rank layout starts from a fresh memset anyway
+    const long long layout = ((long long)c->n << 20) ^ ((long long)a.ctas_total << 8) ^ a.cta0;
+    if (c->sym_priv.cap < bytes || !c->sym_priv_clean || c->sym_layout != layout) {
         GB_TRY(c->sym_priv.reserve(bytes));
         GB_CUDA(cudaMemsetAsync(c->sym_priv.p, 0, c->sym_priv.cap, c->stream));
     }
     a.priv = c->sym_priv.as<double>();
     c->sym_priv_clean = false;
-    // equal masses? (decided on the device, per call: the masses may have been changed by any upload)
+    c->sym_layout = layout;
+    // equal masses?  Decided on the device whenever the masses may have changed (set_system), like the massive list
     GB_TRY(c->sym_flag.reserve(64));
     int *flag = c->sym_flag.as<int>();
     double *mass = reinterpret_cast<double *>(c->sym_flag.as<char>() + 8);
     static const int eqm_allowed = getenv("GRAV_B200_DS_EQUAL_MASS") ? atoi(getenv("GRAV_B200_DS_EQUAL_MASS")) : 1;
-    GB_CUDA(cudaMemsetAsync(flag, 0, 16, c->stream));
-    if (eqm_allowed) {
-        GB_CUDA(cudaMemsetAsync(flag, 1, sizeof(int), c->stream));     // any non-zero value means "equal so far"
-        sym_equal_mass_kernel<<<c->sm_count, 256, 0, c->stream>>>(a.posm, a.n, flag, mass);
-        GB_LAUNCH_CHECK();
-        count_launch();
+    if (!c->sym_eqm_valid) {
+        GB_CUDA(cudaMemsetAsync(flag, 0, 16, c->stream));
+        if (eqm_allowed) {
+            GB_CUDA(cudaMemsetAsync(flag, 1, sizeof(int), c->stream));     // any non-zero value means "equal so far"
+            sym_equal_mass_kernel<<<c->sm_count, 256, 0, c->stream>>>(a.posm, a.n, flag, mass);
+            GB_LAUNCH_CHECK();
+            count_launch();
+        }
+        c->sym_eqm_valid = true;
     }
     a.eqm_flag = flag;
     a.eqm_mass = mass;

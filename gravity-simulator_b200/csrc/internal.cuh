@@ -164,6 +164,8 @@ struct grav_b200_ctx {
     gb::DevBuf sym_priv;  // pair-once direct sum: one private accumulation array per CTA (direct_sum_sym.cu), all zero between calls
     gb::DevBuf sym_flag;  // pair-once direct sum: equal-mass flag + the common mass
     bool sym_priv_clean = false, sym_attr_set = false;
+    long long sym_layout = -1;    // (n, CTAs, first CTA) the private arrays were last used with
+    bool sym_eqm_valid = false;   // sym_flag describes the resident masses (reset with mlist_valid whenever the masses change)
     int last_ds_sym = 0;  // the last pairwise force evaluation took the pair-once path
     gb::DevBuf misc;      // small scratch (reductions)
     // massless method scratch

@@ -863,7 +863,8 @@ int grav_b200_ctx_whfast_begin(grav_b200_ctx *c, const int *particle_ids, int me
         w->pair_max_k = e2 ? (atoi(e2) < WH_PAIR_MAX_K ? atoi(e2) : WH_PAIR_MAX_K) : WH_PAIR_MAX_K;
     }
     c->lf_ready = false;
-    c->mlist_valid = false;      // this integrator reorders (and may remove) particles: posm's masses move
+    c->mlist_valid = false;
+    c->sym_eqm_valid = false;      // this integrator reorders (and may remove) particles: posm's masses move
     // live arrays <- Cartesian state (x unpacked from posm, v, m) + ids
     wh_unpack_kernel<<<WH_GRID(n, 256)>>>(n, c->posm.as<double4>(), w->JX());
     WH_LAUNCHED();

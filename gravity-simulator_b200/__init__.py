@@ -107,7 +107,7 @@ ABI_SYMBOLS = [
     "grav_b200_kernel_launch_count", "grav_b200_measure_fp64_peak", "grav_b200_ctx_event_record",
     "grav_b200_ctx_event_elapsed_ms", "grav_b200_ctx_flush_l2", "grav_b200_ctx_mark_positions_sharded", "grav_b200_ctx_direct_sum_path",
     "grav_b200_host_register", "grav_b200_host_unregister",
-    "grav_b200_compute_energy", "grav_b200_ctx_fixed_begin", "grav_b200_ctx_fixed_steps", "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
+    "grav_b200_compute_energy", "grav_b200_ctx_fixed_begin", "grav_b200_ctx_fixed_steps", "grav_b200_ctx_whfast_begin", "grav_b200_ctx_whfast_set_verbose", "grav_b200_ctx_whfast_steps", "grav_b200_ctx_whfast_get_state", "grav_b200_ctx_whfast_end",
 ]
 SHIM_SYMBOLS = [
     "get_new_acceleration_param", "finalize_acceleration_param", "acceleration", "acceleration_barnes_hut",
@@ -160,6 +160,7 @@ def load():
     abi.grav_b200_ctx_whfast_steps.argtypes = [C.c_void_p, C.c_double, C.c_int64]
     abi.grav_b200_ctx_whfast_get_state.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p]
     abi.grav_b200_ctx_whfast_end.argtypes = [C.c_void_p]
+    abi.grav_b200_ctx_whfast_set_verbose.argtypes = [C.c_void_p, C.c_int]
     abi.grav_b200_ctx_synchronize.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_last_timing_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
     abi.grav_b200_measure_fp64_peak.argtypes = [C.c_int, c_double_p, c_double_p]
@@ -453,6 +454,9 @@ class Context:
                                                          _dp(x), _dp(v), _dp(m)))
         assert nn.value == n
         return {"x": x, "v": v, "m": m, "ids": ids}
+
+    def whfast_set_verbose(self, level):
+        check_rc(self.abi.grav_b200_ctx_whfast_set_verbose(self.h, int(level)))
 
     def whfast_end(self):
         check_rc(self.abi.grav_b200_ctx_whfast_end(self.h))

@@ -227,6 +227,7 @@ int grav_b200_shim_whfast(ErrorStatus *out, System *system, IntegratorParam *int
     TRY_RC(grav_b200_ctx_whfast_begin(ctx, system->particle_ids, acceleration_param->method,
                                       acceleration_param->softening_length, integrator_param->dt,
                                       integrator_param->whfast_remove_invalid_particles));
+    TRY_RC(grav_b200_ctx_whfast_set_verbose(ctx, settings->verbose));   /* the removal message of whfast_drift (:609-623) */
     TRY_RC(whfast_download(ctx, system, 0));     /* the distance-sorted system, as the initial output sees it */
     if (output_param->method != OUTPUT_METHOD_DISABLED && output_param->output_initial)
     {

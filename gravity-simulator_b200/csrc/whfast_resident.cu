@@ -70,6 +70,7 @@ struct WhfastState {
     int method = 0;
     double eps = 0.0;
     bool remove_invalid = false;
+    int verbose = 0;                         // settings->verbose of the caller (GRAV_VERBOSITY_*): >= 3 prints the removal message
     bool ready = false;
     double last_dt = 0.0;
 
@@ -791,6 +792,30 @@ static int wh_steps_plain_or_graph(grav_b200_ctx *c, WhfastState *w, double dt, 
     return GRAV_B200_OK;
 }
 
+// The reference's message before a removal (src/integrator_whfast.c:609-623, verbose >= GRAV_VERBOSITY_VERBOSE): ids of the
+// flagged particles in index order.  The host is synchronised here anyway (it just read the status words).
+static int wh_print_removed(grav_b200_ctx *c, WhfastState *w, int n_removed)
+{
+    const int n = c->n;
+    char *bad = (char *)malloc((size_t)n);
+    int *ids = (int *)malloc(sizeof(int) * (size_t)n);
+    if (!bad || !ids) { free(bad); free(ids); set_error("out of host memory"); return GRAV_B200_ECUDA; }
+    cudaError_t e = cudaMemcpyAsync(bad, w->bad.as<char>(), (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ids, w->IDS(), sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { free(bad); free(ids); return cuda_fail(e, "download of the removal flags", __FILE__, __LINE__); }
+    fprintf(stderr, "whfast_drift: Removing %d invalid particles. Particle IDs: [", n_removed);
+    bool first = true;
+    for (int i = 0; i < n; i++) {
+        if (!bad[i]) continue;
+        fprintf(stderr, first ? "%d" : ", %d", ids[i]);
+        first = false;
+    }
+    fputs("]\n", stderr);
+    free(bad); free(ids);
+    return GRAV_B200_OK;
+}
+
 // the removal itself (:607-671): stable compaction of the Jacobi state, masses and ids; eta recomputed
 static int wh_remove_flagged(grav_b200_ctx *c, WhfastState *w, int n_removed)
 {
@@ -910,6 +935,14 @@ int grav_b200_ctx_whfast_begin(grav_b200_ctx *c, const int *particle_ids, int me
     return GRAV_B200_OK;
 }
 
+int grav_b200_ctx_whfast_set_verbose(grav_b200_ctx *c, int level)
+{
+    WhfastState *w = c ? (WhfastState *)c->wh : nullptr;
+    if (!w) { set_error("whfast_begin() has not been called"); return GRAV_B200_EINVAL; }
+    w->verbose = level;
+    return GRAV_B200_OK;
+}
+
 int grav_b200_ctx_whfast_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
 {
     WhfastState *w = c ? (WhfastState *)c->wh : nullptr;
@@ -945,6 +978,7 @@ int grav_b200_ctx_whfast_steps(grav_b200_ctx *c, double dt, int64_t num_steps)
         GB_TRY(wh_read_status(c, w));
         const int n_removed = w->h_status[2];
         if (n_removed <= 0 || n_removed >= n) { set_error("whfast replay lost the flagged particles (%d of %d)", n_removed, n); return GRAV_B200_ECUDA; }
+        if (w->verbose >= 3) GB_TRY(wh_print_removed(c, w, n_removed));
         GB_TRY(wh_remove_flagged(c, w, n_removed));
         GB_TRY(wh_step_back(c, w, dt));
         remaining -= (first_bad + 1);

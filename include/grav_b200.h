@@ -224,10 +224,14 @@ int grav_b200_ctx_fixed_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
  *   whfast_end():   releases the integrator state.
  * Ordering assumptions behind "bit-identical": equal distances keep index order (stable sort -- glibc's qsort is a stable
  * merge sort for these sizes; the C standard leaves tie order open) and invalid particles are removed in ascending index
- * order (the reference's serial order; its OpenMP build fills the removal list in thread-arrival order).  The reference's
- * verbose-mode diagnostics of whfast_drift are not printed by this loop. */
+ * order (the reference's serial order; its OpenMP build fills the removal list in thread-arrival order).
+ *   whfast_set_verbose(): the caller's Settings.verbose.  At GRAV_VERBOSITY_VERBOSE (3) a removal prints the reference's
+ *                   "whfast_drift: Removing N invalid particles. Particle IDs: [...]" line (:609-623) to stderr.  The
+ *                   per-particle "Kepler's equation did not converge" lines and the Stumpff NaN/Inf warning (:486-549)
+ *                   are not printed by this loop (the iteration's error value stays on the device). */
 int grav_b200_ctx_whfast_begin(grav_b200_ctx *ctx, const int *particle_ids, int method, double softening_length,
                                double dt, int remove_invalid_particles);
+int grav_b200_ctx_whfast_set_verbose(grav_b200_ctx *ctx, int level);
 int grav_b200_ctx_whfast_steps(grav_b200_ctx *ctx, double dt, int64_t num_steps);
 int grav_b200_ctx_whfast_get_state(grav_b200_ctx *ctx, int snapshot, int *n_out, int *particle_ids, double *x,
                                    double *v, double *m);

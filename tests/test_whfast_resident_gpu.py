@@ -69,6 +69,34 @@ def test_resident_whfast_removes_invalid_particles(gb, oracle, ics, k, grazers, 
     _same(got, ref)
 
 
+def test_resident_whfast_removal_message(gb, oracle, ics, capfd):
+    """With the caller's Settings.verbose at GRAV_VERBOSITY_VERBOSE a removal prints the reference's line
+    (src/integrator_whfast.c:609-623): the count and the ids of the removed particles in index order.  The ids named over
+    the whole run are exactly the particles the oracle's run lost; nothing is printed at a lower level."""
+    import re
+    x, v, m, G = ics.asteroid_belt(2000, 5, grazers=40)
+    ref = oracle.whfast_integrate(x, v, m, G, 180.0, 180.0 * 6, "massless", 0.0, True)
+    lost = sorted(set(range(m.shape[0])) - set(int(i) for i in ref["ids"]))
+    assert lost
+    for level in (3, 2):
+        with gb.Context() as c:
+            c.set_system(x, m, G, v)
+            c.whfast_begin(180.0, "massless", 0.0, True)
+            c.whfast_set_verbose(level)
+            capfd.readouterr()
+            c.whfast_steps(180.0, 6)
+            got = c.whfast_state(snapshot=False)
+            c.whfast_end()
+        err = capfd.readouterr().err
+        _same(got, ref)
+        lines = re.findall(r"whfast_drift: Removing (\d+) invalid particles\. Particle IDs: \[([0-9, ]+)\]", err)
+        if level < 3:
+            assert not lines
+            continue
+        named = [int(t) for _, ids in lines for t in ids.split(",")]
+        assert sorted(named) == lost and all(int(cnt) == len(ids.split(",")) for cnt, ids in lines)
+
+
 def test_resident_whfast_without_removal(gb, oracle, ics):
     """whfast_remove_invalid_particles = false: no checkpoints, no replays, one long queue of steps."""
     x, v, m, G = ics.asteroid_belt(3000, 21)

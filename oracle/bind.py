@@ -9,6 +9,7 @@ never by the product package.  Two libraries:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -447,7 +448,8 @@ def launch_simulation(lib_path, x, v, m, G, tf, integrator="leapfrog", dt=1e-3, 
     new_ids = C.POINTER(C.c_int32)(); new_x = dp(); new_v = dp(); new_m = dp()
     is_exit = C.c_bool(False)
     L.launch_simulation_python.restype = C.c_int
-    if integrator == "whfast":
+    # (not for the drop-in build's resident loop, which never runs the reference's whfast(): keeps its timings undisturbed)
+    if integrator == "whfast" and (str(lib_path) != str(DROPIN_SO) or os.environ.get("GRAV_B200_RESIDENT") == "0"):
         with zeroed_malloc():
             return _launch_simulation_call(L, n, ids, x, v, m, new_ids, new_x, new_v, new_m, G, integrator, dt, tolerance, remove_invalid,
                                            method, opening_angle, softening_length, max_num_particles_per_leaf, output_dir,

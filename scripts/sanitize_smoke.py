@@ -50,6 +50,24 @@ abi.grav_b200_set_bh_exact(0)
 xc = x.copy(); xc[3] = xc[700]
 gb.compute_energy(xc, v, m, G)
 x, v, m, G = ics.plummer(40000, 1)
-gb.acceleration(x, m, G, "pairwise", 0.01)      # fast kernel + fix-up + special-tile kernel
+abi.grav_b200_set_direct_sum_mode(0)
+gb.acceleration(x, m, G, "pairwise", 0.01)      # ordered interactions: fast kernel + fix-up + special-tile kernel
+abi.grav_b200_set_direct_sum_mode(-1)
 gb.acceleration(x, m, G, "barnes_hut", 0.01, 0.5, 1)
+# second half of round 2: the pair-once direct sum (rotation loop, cp.async slices, private arrays + finishing kernel), equal
+# and unequal masses, with and without softening (masked last group), forced for small systems and chosen automatically
+abi.grav_b200_set_direct_sum_mode(1)
+for n in (513, 1000, 3001):
+    xs, vs, ms, Gs = ics.plummer(n, n)
+    for mm in (ms, ms * np.random.default_rng(n).uniform(0.5, 1.5, n)):
+        for eps in (0.01, 0.0):
+            assert np.isfinite(gb.acceleration(xs, mm, Gs, "pairwise", eps)).all()
+abi.grav_b200_set_direct_sum_mode(-1)
+xs, vs, ms, Gs = ics.plummer(12500, 4)
+with gb.Context() as c:
+    c.set_system(xs, ms, Gs, vs)
+    c.acceleration("pairwise", 0.01); c.acceleration("pairwise", 0.01)
+    assert c.direct_sum_path()[0]
+    c.energy()                                   # pair-once energy kernel (mirrored blocks)
+    c.accelerations()
 print("sanitize_smoke done")

@@ -368,7 +368,11 @@ int direct_sum_pairwise(grav_b200_ctx *c, double eps)
 {
     // large systems: every unordered pair once (direct_sum_sym.cu), 10 instead of 16 FP64 instructions per ordered interaction
     c->last_ds_sym = direct_sum_sym_wanted(c) ? 1 : 0;
-    if (c->last_ds_sym) return direct_sum_pairwise_sym(c, eps);
+    if (c->last_ds_sym) {
+        const int rc = direct_sum_pairwise_sym(c, eps);
+        if (rc != GRAV_B200_ENOMEM_SYM) return rc;
+        c->last_ds_sym = 0;      // no room for the private accumulation arrays on this device: ordered interactions instead
+    }
     DSArgs a{};
     a.src = c->posm.as<double4>();
     a.n_src = c->n;

@@ -426,7 +426,10 @@ int direct_sum_pairwise_sym(grav_b200_ctx *c, double eps)
     // system size or rank layout starts from a fresh memset anyway
     const long long layout = ((long long)c->n << 20) ^ ((long long)a.ctas_total << 8) ^ a.cta0;
     if (c->sym_priv.cap < bytes || !c->sym_priv_clean || c->sym_layout != layout) {
-        GB_TRY(c->sym_priv.reserve(bytes));
+        if (c->sym_priv.reserve(bytes) != GRAV_B200_OK) {
+            cudaGetLastError();
+            return GRAV_B200_ENOMEM_SYM;
+        }
         GB_CUDA(cudaMemsetAsync(c->sym_priv.p, 0, c->sym_priv.cap, c->stream));
     }
     a.priv = c->sym_priv.as<double>();

@@ -202,6 +202,7 @@ namespace gb {
 int direct_sum_pairwise(grav_b200_ctx *c, double eps);
 int direct_sum_massless(grav_b200_ctx *c, double eps);
 // direct_sum_sym.cu
+constexpr int GRAV_B200_ENOMEM_SYM = -1000;   // internal: the private arrays of the pair-once kernel could not be allocated
 bool direct_sum_sym_wanted(const grav_b200_ctx *c);
 int direct_sum_pairwise_sym(grav_b200_ctx *c, double eps);
 int direct_sum_small_host(grav_b200_ctx *c, double *a, int n, const double *x, const double *m, double G, double eps);

@@ -426,7 +426,9 @@ int direct_sum_pairwise_sym(grav_b200_ctx *c, double eps)
     // system size or rank layout starts from a fresh memset anyway
     const long long layout = ((long long)c->n << 20) ^ ((long long)a.ctas_total << 8) ^ a.cta0;
     if (c->sym_priv.cap < bytes || !c->sym_priv_clean || c->sym_layout != layout) {
-        if (c->sym_priv.reserve(bytes) != GRAV_B200_OK) {
+        const int rc_alloc = c->sym_priv.reserve(bytes);
+        if (rc_alloc != GRAV_B200_OK) {
+            if (c->world > 1) return rc_alloc;     // the ranks must take the same path (collectives): report, do not switch
             cudaGetLastError();
             return GRAV_B200_ENOMEM_SYM;
         }

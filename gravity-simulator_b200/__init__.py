@@ -96,7 +96,8 @@ ABI_SYMBOLS = [
     "grav_b200_acceleration_massless", "grav_b200_acceleration_barnes_hut",
     "grav_b200_whfast_acceleration_pairwise", "grav_b200_whfast_acceleration_massless",
     "grav_b200_construct_octree", "grav_b200_morton_keys", "grav_b200_set_bh_mode", "grav_b200_get_bh_mode",
-    "grav_b200_set_bh_exact", "grav_b200_get_bh_exact", "grav_b200_set_direct_sum_mode", "grav_b200_get_direct_sum_mode",
+    "grav_b200_set_bh_exact", "grav_b200_get_bh_exact", "grav_b200_set_direct_sum_mode", "grav_b200_get_direct_sum_mode", "grav_b200_debug_pair_once_segments",
+    "grav_b200_debug_pair_once_touches", "grav_b200_debug_pair_once_row",
     "grav_b200_ctx_create_team", "grav_b200_ctx_create_auto",
     "grav_b200_ctx_team_size",
     "grav_b200_ctx_create", "grav_b200_ctx_destroy", "grav_b200_nccl_unique_id", "grav_b200_ctx_set_system",
@@ -168,6 +169,8 @@ def load():
     abi.grav_b200_ctx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     abi.grav_b200_ctx_flush_l2.argtypes = [C.c_void_p]
     abi.grav_b200_ctx_mark_positions_sharded.argtypes = [C.c_void_p]
+    abi.grav_b200_debug_pair_once_segments.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p]
+    abi.grav_b200_debug_pair_once_touches.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     abi.grav_b200_ctx_direct_sum_path.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     abi.grav_b200_host_register.argtypes = [C.c_void_p, C.c_uint64]
     abi.grav_b200_host_unregister.argtypes = [C.c_void_p]

@@ -25,7 +25,7 @@
 // leaves the arrays zeroed for the next call.  With several ranks each one does its share of the units and of the
 // diagonal blocks for ALL particles and the results are added with one all-reduce of 24 n bytes.
 //
-// Tuning (profiles/r2_sym_variants.txt): 8 particles per lane at 240 registers and 8 warps per SM beat 4 per lane at
+// Tuning (profiles/r2_sym_variants.txt; the SY_*_ macros are the knobs of scripts/build_variant.sh): 8 particles per lane at 240 registers and 8 warps per SM beat 4 per lane at
 // 128 registers and 16 warps by 8 % -- the FP64 chains of 8 independent pairs hide the pipe latency better than more
 // warps do; reading the next j-position one step ahead is worth 7 % of that.
 #include "internal.cuh"
@@ -40,12 +40,6 @@ namespace gb {
 #endif
 #ifndef SY_UNROLL_
 #define SY_UNROLL_ 1
-#endif
-#ifndef SY_PF_
-#define SY_PF_ 1
-#endif
-#ifndef SY_SPLITJ_
-#define SY_SPLITJ_ 0
 #endif
 constexpr int SY_TI = SY_TI_;            // particles per lane in a row
 constexpr int SY_ROW = 32 * SY_TI;       // 256
@@ -132,46 +126,24 @@ __device__ __forceinline__ void sym_group(const double4 *__restrict__ sl, int jb
                                           double (&ay)[SY_TI], double (&az)[SY_TI], double &ajx, double &ajy, double &ajz)
 {
     const int lane = threadIdx.x & 31;
-#if SY_PF_
-    double4 pn = sl[lane];                   // the j-particle of the next step is read one step ahead
-#endif
-#if SY_SPLITJ_
-    double bjx = 0.0, bjy = 0.0, bjz = 0.0;  // second chain of j-accumulators (pairs t >= SY_TI / 2)
-#endif
+    double4 pn = sl[lane];                   // the j-particle of a step is read one step ahead (+7 %)
 #pragma unroll SY_UNROLL
     for (int s = 0; s < 32; s++) {
         const int jj = (lane + s) & 31;
-#if SY_PF_
         const double4 pj = pn;
         pn = sl[(lane + s + 1) & 31];
-#else
-        const double4 pj = sl[jj];
-#endif
         const bool jv = CHECK ? (jbase + jj < n) : true;
 #pragma unroll
-        for (int t = 0; t < SY_TI; t++) {
-#if SY_SPLITJ_
-            if (t >= SY_TI / 2) sym_pair<EQM, CHECK>(xi[t], yi[t], zi[t], mi[t], pj, jv, eps2, ax[t], ay[t], az[t], bjx, bjy, bjz);
-            else
-#endif
+        for (int t = 0; t < SY_TI; t++)
             sym_pair<EQM, CHECK>(xi[t], yi[t], zi[t], mi[t], pj, jv, eps2, ax[t], ay[t], az[t], ajx, ajy, ajz);
-        }
         // the accumulators of j-particle (lane + s) & 31 move on to the lane that meets it next
         ajx = __shfl_sync(0xffffffffu, ajx, (lane + 1) & 31);
         ajy = __shfl_sync(0xffffffffu, ajy, (lane + 1) & 31);
         ajz = __shfl_sync(0xffffffffu, ajz, (lane + 1) & 31);
-#if SY_SPLITJ_
-        bjx = __shfl_sync(0xffffffffu, bjx, (lane + 1) & 31);
-        bjy = __shfl_sync(0xffffffffu, bjy, (lane + 1) & 31);
-        bjz = __shfl_sync(0xffffffffu, bjz, (lane + 1) & 31);
-#endif
     }
-#if SY_SPLITJ_
-    ajx += bjx; ajy += bjy; ajz += bjz;
-#endif
 }
 
-// One segment = groups [ka, kb) of row A (absolute group 4(A+1) + k), shared round-robin by the warps of the CTA.
+// One segment = groups [ka, kb) of row A (absolute group SY_GPR (A+1) + k), shared round-robin by the warps of the CTA.
 template <bool EQM>
 __device__ __forceinline__ void sym_segment(const SymArgs &p, int A, int ka, int kb, double4 *slice, double *part, double *P)
 {
@@ -264,7 +236,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) direct_sum_sym_kernel(const Sym
 // Whether CTA cg of the decomposition added anything to the entries of block b (particles [b SY_ROW, (b+1) SY_ROW)): as one
 // of its rows (i-side) or inside the group ranges it met (j-side).  May say yes for a CTA that did not (reading zeros is
 // harmless); never says no for one that did -- the finishing kernel leaves exactly the touched entries zeroed.
-__device__ inline bool sym_cta_touches(const SymArgs &p, long long cg, int b)
+__host__ __device__ inline bool sym_cta_touches(const SymArgs &p, long long cg, int b)
 {
     const long long u0 = sym_unit_begin(cg, p.U, p.ctas_total), u1 = sym_unit_begin(cg + 1, p.U, p.ctas_total);
     if (u0 >= u1) return false;
@@ -474,3 +446,50 @@ int direct_sum_pairwise_sym(grav_b200_ctx *c, double eps)
 }
 
 }  // namespace gb
+
+// ---- test hooks (host code only: the decomposition the kernels use, so that it can be checked without a GPU) ------------
+extern "C" {
+
+// Segments of CTA `cta` of `ctas_total` for a system of n particles: up to max_segments triples (row, first group, end group)
+// with absolute group indices; returns the number of segments, or -1 for a system without two rows.
+int grav_b200_debug_pair_once_segments(int n, int ctas_total, int cta, int max_segments, int *rows, int *group_begin, int *group_end)
+{
+    using namespace gb;
+    const int NR = (n + SY_ROW - 1) / SY_ROW, NG = (n + 31) / 32;
+    if (NR < 2) return -1;
+    const long long U = sym_row_start(NR - 1, NG);
+    long long u = sym_unit_begin(cta, U, ctas_total);
+    const long long u1 = sym_unit_begin(cta + 1LL, U, ctas_total);
+    int count = 0;
+    while (u < u1) {
+        const int A = sym_row_of(u, NG, NR);
+        const long long rs = sym_row_start(A, NG);
+        const int L = NG - SY_GPR * (A + 1);
+        const int ka = (int)(u - rs);
+        const long long rem = u1 - rs;
+        const int kb = rem < (long long)L ? (int)rem : L;
+        if (count < max_segments) { rows[count] = A; group_begin[count] = SY_GPR * (A + 1) + ka; group_end[count] = SY_GPR * (A + 1) + kb; }
+        count++;
+        u = rs + kb;
+    }
+    return count;
+}
+
+// Whether the finishing kernel reads CTA `cta`'s private array for block `block` (SY_ROW particles): sym_cta_touches().
+int grav_b200_debug_pair_once_touches(int n, int ctas_total, int cta, int block)
+{
+    using namespace gb;
+    SymArgs a{};
+    a.n = n;
+    a.NR = (n + SY_ROW - 1) / SY_ROW;
+    a.NG = (n + 31) / 32;
+    if (a.NR < 2) return -1;
+    a.U = sym_row_start(a.NR - 1, a.NG);
+    a.cta0 = 0;
+    a.ctas_total = ctas_total;
+    return sym_cta_touches(a, cta, block) ? 1 : 0;
+}
+
+int grav_b200_debug_pair_once_row(void) { return gb::SY_ROW; }
+
+}  // extern "C"

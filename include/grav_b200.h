@@ -139,6 +139,13 @@ int grav_b200_get_bh_exact(void);
  * Both agree with the reference to <= 1e-12 relative.  Also settable with GRAV_B200_DS_SYM (read once). */
 int grav_b200_set_direct_sum_mode(int mode);
 int grav_b200_get_direct_sum_mode(void);
+/* Test hooks (host code, no GPU needed): the work decomposition of the pair-once kernel (direct_sum_sym.cu).
+ * _segments: the (row, [group_begin, group_end)) pieces CTA `cta` of `ctas_total` works through for a system of n particles
+ * (rows of _row() particles, groups of 32; returns how many, -1 if the system has fewer than two rows); _touches: whether
+ * the finishing kernel reads that CTA's private sums for block `block` of _row() particles. */
+int grav_b200_debug_pair_once_segments(int n, int ctas_total, int cta, int max_segments, int *rows, int *group_begin, int *group_end);
+int grav_b200_debug_pair_once_touches(int n, int ctas_total, int cta, int block);
+int grav_b200_debug_pair_once_row(void);
 
 /* ---- (2) device-resident context ---------------------------------------------------- */
 

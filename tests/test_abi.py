@@ -85,3 +85,57 @@ def test_no_cpu_fallback(gb):
         gb.Context()
     with pytest.raises(gb.GravB200Error):
         gb.construct_octree(x, m)
+
+
+@pytest.mark.parametrize("n", [512, 513, 777, 1000, 2049, 4099, 8192, 20001, 65536])
+@pytest.mark.parametrize("ctas", [1, 7, 148, 296, 1184])
+def test_pair_once_decomposition_covers_every_pair_once(gb, n, ctas):
+    """Host code of direct_sum_sym.cu through its test hooks (no GPU): over all CTAs of the decomposition (one GPU: 148;
+    8 GPUs: 1184) every (row, group beyond the row) unit is handed out exactly once, i.e. every unordered pair of particles
+    in different rows is evaluated exactly once (pairs inside a row are the finishing kernel's diagonal blocks); and the
+    finishing kernel's contributor test (sym_cta_touches) names exactly the CTAs that added something to a block, so the
+    private arrays are read completely and left zeroed."""
+    abi, _ = gb.load()
+    row = abi.grav_b200_debug_pair_once_row()
+    gpr = row // 32
+    NR, NG = -(-n // row), -(-n // 32)
+    cap = 4096
+    rows = (C.c_int * cap)(); gb_ = (C.c_int * cap)(); ge = (C.c_int * cap)()
+    seen = np.zeros((NR, NG), dtype=np.int32)
+    touched = np.zeros((ctas, NR), dtype=bool)
+    for c in range(ctas):
+        k = abi.grav_b200_debug_pair_once_segments(n, ctas, c, cap, rows, gb_, ge)
+        assert 0 <= k <= cap
+        for s in range(k):
+            A, g0, g1 = rows[s], gb_[s], ge[s]
+            assert 0 <= A < NR - 1 and gpr * (A + 1) <= g0 < g1 <= NG
+            seen[A, g0:g1] += 1
+            touched[c, A] = True
+            touched[c, g0 // gpr:(g1 - 1) // gpr + 1] = True
+    expect = np.zeros_like(seen)
+    for A in range(NR - 1):
+        expect[A, gpr * (A + 1):] = 1
+    assert np.array_equal(seen, expect)
+    claimed = np.array([[abi.grav_b200_debug_pair_once_touches(n, ctas, c, b) for b in range(NR)] for c in range(ctas if ctas <= 296 else 64)])
+    assert np.array_equal(claimed.astype(bool), touched[:claimed.shape[0]])
+
+
+def test_zeroed_malloc_for_the_reference_whfast():
+    """oracle/bind.py zeroed_malloc: while it is active glibc hands out zero-filled blocks (what the reference's whfast()
+    implicitly relies on for a[0])."""
+    from oracle.bind import zeroed_malloc
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.free.argtypes = [C.c_void_p]
+    blocks = []
+    for _ in range(50):                      # dirty a few free chunks first
+        p = libc.malloc(12216)
+        C.memset(p, 0x5A, 12216)
+        blocks.append(p)
+    for p in blocks:
+        libc.free(p)
+    with zeroed_malloc():
+        p = libc.malloc(12216)
+        buf = (C.c_ubyte * 12216).from_address(p)
+        assert not any(buf)
+        libc.free(p)

@@ -190,3 +190,19 @@ def test_formulations_agree_at_size(gb, ics):
             c.acceleration("pairwise", 0.01)
             assert c.direct_sum_path()[0]
             assert np.array_equal(c.accelerations(), a1)
+
+
+def test_pair_once_two_million_particles_sampled(gb, oracle, ics):
+    """N = 2^21 + 77 (ragged; 148 private accumulation arrays of 50 MB each = 7.4 GB, 64-bit offsets everywhere): sampled targets
+    against the reference's summation order, unequal masses so that the general loop runs."""
+    n = (1 << 21) + 77
+    x, v, m, G = ics.plummer(n, 5)
+    m = m * np.random.default_rng(5).uniform(0.5, 1.5, n)
+    tg = np.concatenate([np.arange(8), np.arange(n - 8, n), np.random.default_rng(6).choice(n, 240, replace=False)]).astype(np.int32)
+    with gb.Context() as c:
+        c.set_system(x, m, G, v)
+        c.acceleration("pairwise", 0.01)
+        assert c.direct_sum_path() == (True, False)
+        a = c.accelerations()
+    assert np.isfinite(a).all()
+    assert max_rel_err(a[tg], oracle.pairwise_targets(x, m, G, 0.01, tg)) <= TOL

@@ -559,7 +559,7 @@ def run_b200_arm(args):
             ctx.event_record(7)
             e_ms = ctx.event_elapsed_ms(6, 7)
             en = {"metric": "energy_eval_ms", "value": e_ms, "unit": "ms", "n": ne, "G_pairs_per_s": ne * (ne - 1.0) / (e_ms * 1e-3) / 1e9,
-                  "note": "13 FP64-pipe instructions per ordered pair (rsqrt seed + one correction), the direct sum's tile loop with a scalar reduction"}
+                  "note": "every unordered pair once, 13 FP64-pipe instructions per pair (rsqrt seed + one correction): the direct sum's tile loop over mirrored target blocks with a scalar reduction; G_pairs_per_s counts ordered-pair equivalents N(N-1)"}
         except gb.GravB200Error as e:
             en = {"unavailable": str(e)[:200]}
 

@@ -206,8 +206,9 @@ int synced_velocities(grav_b200_ctx *c, double **d_out)
 // q is), and the ranks of a multi-GPU run take the q in turn.  The kinetic term is summed over the rank's own targets
 // (velocities are sharded).  Block partial sums are written out and added in block order by one thread: deterministic.
 // Coincident particles give a non-finite energy like the reference's 1/0.
+// tiles [tile_lo, tile_hi) (256 sources each, absolute indices) against target block blk
 template <int TI>
-__device__ __forceinline__ double energy_block_potential(const double4 *__restrict__ posm, int n, int n_pad, int blk, double4 *tile)
+__device__ __forceinline__ double energy_block_potential(const double4 *__restrict__ posm, int n, int blk, int tile_lo, int tile_hi, double4 *tile)
 {
     double xi[TI], yi[TI], zi[TI], mi[TI], pot[TI];
     int ii[TI];
@@ -218,7 +219,8 @@ __device__ __forceinline__ double energy_block_potential(const double4 *__restri
         xi[t] = me.x; yi[t] = me.y; zi[t] = me.z; mi[t] = me.w;
         pot[t] = 0.0;
     }
-    for (int j0 = blk * TI * 256; j0 < n_pad; j0 += 256) {
+    for (int jt = tile_lo; jt < tile_hi; jt++) {
+        const int j0 = jt * 256;
         __syncthreads();
         tile[threadIdx.x] = posm[j0 + threadIdx.x];
         __syncthreads();
@@ -244,9 +246,9 @@ __device__ __forceinline__ double energy_block_potential(const double4 *__restri
     for (int t = 0; t < TI; t++) {
         if (ii[t] < n && pot[t] != pot[t]) {
             // r = 0 (another particle at the same point) turns the seed into inf and the correction into NaN; the reference
-            // divides by zero there (m / 0 = inf, or NaN for a massless partner): repeat this one target with the division
+            // divides by zero there (m / 0 = inf, or NaN for a massless partner): repeat this target's share with the division
             double p = 0.0;
-            for (int j = ii[t] + 1; j < n; j++) {
+            for (int j = max(ii[t] + 1, tile_lo * 256); j < min(n, tile_hi * 256); j++) {
                 const double4 q = posm[j];
                 const double dx = q.x - xi[t], dy = q.y - yi[t], dz = q.z - zi[t];
                 p += q.w / sqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
@@ -255,21 +257,29 @@ __device__ __forceinline__ double energy_block_potential(const double4 *__restri
         }
         if (ii[t] < n) e -= mi[t] * pot[t];
     }
-    return e;      // - sum over the block's targets of m_i sum_{j>i} m_j / r_ij   (G applied by the caller)
+    return e;      // - sum over the block's targets of m_i sum_{j>i, j in the tiles} m_j / r_ij   (G applied by the caller)
 }
 
+// Work item = (mirrored pair q of target blocks, split s of `splits`): the NT - b TI tiles of block q followed by those of block
+// NB - 1 - q form one list of ~NT + TI tiles whatever q is; the item takes the s-th share of that list.  The splits only serve
+// the balance: 256 equal pairs on 148 SMs would run as long as 296.
 template <int TI>
 __global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__ posm, const double *__restrict__ v, int n, int n_pad,
-                                                    int lo, int hi, int rank, int world, double G, double *__restrict__ block_out)
+                                                    int lo, int hi, int rank, int world, int splits, double G,
+                                                    double *__restrict__ block_out)
 {
     __shared__ double4 tile[256];
     __shared__ double red[256];
-    const int NB = (n + 256 * TI - 1) / (256 * TI);
-    const int q = blockIdx.x * world + rank;           // this CTA's target block and, mirrored, its partner
+    const int NB = (n + 256 * TI - 1) / (256 * TI), NT = n_pad / 256;
+    const int item = blockIdx.x * world + rank;
+    const int q = item / splits, s = item - q * splits;
     double e = 0.0;
     if (q < (NB + 1) / 2) {
-        e = energy_block_potential<TI>(posm, n, n_pad, q, tile);
-        if (NB - 1 - q != q) e += energy_block_potential<TI>(posm, n, n_pad, NB - 1 - q, tile);
+        const int b0 = q, b1 = NB - 1 - q;
+        const int T0 = NT - b0 * TI, T1 = (b1 != b0) ? NT - b1 * TI : 0;
+        const int a = (int)(((long long)s * (T0 + T1)) / splits), z = (int)(((long long)(s + 1) * (T0 + T1)) / splits);
+        if (a < T0) e = energy_block_potential<TI>(posm, n, b0, b0 * TI + a, b0 * TI + min(z, T0), tile);
+        if (z > T0) e += energy_block_potential<TI>(posm, n, b1, b1 * TI + max(a - T0, 0), b1 * TI + (z - T0), tile);
         e *= G;
     }
     // kinetic energy of the rank's own targets, spread over the CTAs
@@ -279,8 +289,8 @@ __global__ void __launch_bounds__(256) energy_kernel(const double4 *__restrict__
     }
     red[threadIdx.x] = e;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
         __syncthreads();
     }
     if (threadIdx.x == 0) block_out[blockIdx.x] = red[0];
@@ -440,14 +450,19 @@ int grav_b200_ctx_energy(grav_b200_ctx *c, double *energy)
     GB_TRY(synced_velocities(c, &d_v));
     // every unordered pair once: a CTA takes a block of targets and its mirror image, the ranks take the CTAs in turn.
     // Four targets per thread once that still leaves two CTAs per SM; one target per thread below (small systems need the CTAs)
-    auto ctas_for = [&](int ti) { const int nb = (c->n + 256 * ti - 1) / (256 * ti); const int pairs = (nb + 1) / 2; return (pairs + c->world - 1) / c->world; };
-    const bool ti4 = ctas_for(4) >= 2 * c->sm_count;
-    const int blocks = ti4 ? ctas_for(4) : ctas_for(1);
+    auto pairs_for = [&](int ti) { const int nb = (c->n + 256 * ti - 1) / (256 * ti); return (nb + 1) / 2; };
+    const bool ti4 = (pairs_for(4) + c->world - 1) / c->world >= 2 * c->sm_count;
+    const int pairs = ti4 ? pairs_for(4) : pairs_for(1);
+    // split the pairs' tile lists until a rank has at least ~6 items per SM (rounding loss of the last wave < 15 %)
+    int splits = 1;
+    const int NT = c->n_pad / 256;
+    while (splits < 16 && splits * 2 <= NT && (long long)pairs * splits < 6LL * c->sm_count * c->world) splits *= 2;
+    const int blocks = (int)(((long long)pairs * splits + c->world - 1) / c->world);
     GB_TRY(c->misc.reserve(sizeof(double) * ((size_t)blocks + 2)));
     double *part = c->misc.as<double>();
     if (blocks > 0) {
-        if (ti4) energy_kernel<4><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->rank, c->world, c->G, part + 1);
-        else energy_kernel<1><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->rank, c->world, c->G, part + 1);
+        if (ti4) energy_kernel<4><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->rank, c->world, splits, c->G, part + 1);
+        else energy_kernel<1><<<blocks, 256, 0, c->stream>>>(c->posm.as<double4>(), d_v, c->n, c->n_pad, c->lo, c->hi, c->rank, c->world, splits, c->G, part + 1);
         GB_LAUNCH_CHECK();
         count_launch();
     }

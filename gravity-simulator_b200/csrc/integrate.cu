@@ -202,10 +202,12 @@ int synced_velocities(grav_b200_ctx *c, double **d_out)
 // r2^-1/2 = y0 (1 + e (1/2 + 3/8 e)) -- the dropped term 5/16 e^3 is < 2^-61 -- i.e. 13 FP64-pipe instructions per
 // pair instead of the ~45 of sqrt + division.  Every unordered pair is visited ONCE, like the reference's i < j loop: a
 // target sums m_j / r_ij over the sources j > i only, so a block of targets streams the tiles from its own onwards.  To
-// keep the CTAs equally loaded a CTA takes target block q and its mirror image NB - 1 - q (together NT + 1 tiles whatever
-// q is), and the ranks of a multi-GPU run take the q in turn.  The kinetic term is summed over the rank's own targets
+// keep the CTAs equally loaded the unit of work is target block q TOGETHER with its mirror image NB - 1 - q (NT + TI tiles
+// whatever q is), cut into a few equal shares of that tile list (energy_kernel below); the ranks of a multi-GPU run take
+// the work items in turn.  The kinetic term is summed over the rank's own targets
 // (velocities are sharded).  Block partial sums are written out and added in block order by one thread: deterministic.
 // Coincident particles give a non-finite energy like the reference's 1/0.
+
 // tiles [tile_lo, tile_hi) (256 sources each, absolute indices) against target block blk
 template <int TI>
 __device__ __forceinline__ double energy_block_potential(const double4 *__restrict__ posm, int n, int blk, int tile_lo, int tile_hi, double4 *tile)

@@ -87,3 +87,14 @@ def test_reference_arm_rank0_only():
     assert len(lines) == 1
     d = lines[0]
     assert d["impl"] == "reference" and d["cpu_baseline"]["cores"] == 1 and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_roofline_bookkeeping():
+    """bench.py's host-side bookkeeping for the pair-once kernel (no GPU): the DRAM traffic it reports comes from the committed
+    ncu metrics file, and the instruction counts per ordered interaction of the three paths are the ones DESIGN.md section 4.1
+    derives (16 ordered; 20 and 18 per unordered pair)."""
+    import bench
+    t = bench.sym_ncu_traffic()
+    assert t is not None and 5e10 < t < 2e11          # 57 GB read + 52 GB written at N = 2^20 (profiles/r2_sym_n1m.txt)
+    assert bench.FP64_OPS == {"ordered": 16.0, "pair_once": 10.0, "pair_once_equal_mass": 9.0}
+    assert bench.FLOP_PER_INTERACTION == 20
